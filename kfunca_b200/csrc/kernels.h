@@ -1,0 +1,115 @@
+// Plain-C++ launch entry points of the sm_100a kernels (defined in kernels/*.cu).  Everything is
+// issued on Runtime::stream().  These replace the reference's "kernel entry" headers
+// src/device/include/*.h (SURVEY §8b inner boundary).
+#pragma once
+#include <cstdint>
+
+#include "core.h"
+
+namespace kf {
+
+constexpr int kPlanDims = KF_MAX_DIMS;
+
+enum EwOp : int {
+    EW_ADD = 0, EW_SUB = 1, EW_MUL = 2, EW_DIV = 3,  // binary   (ref: binary_ops_kernel.cu:6-60)
+    EW_COPY = 4,                                     // unary    (ref: unary_ops_kernel.cu:6-17)
+    EW_FILL = 5,                                     // nullary  (ref: nullary_ops_kernel.cu:6-25)
+    EW_SQRT = 6, EW_RSQRT = 7, EW_NEG = 8,           // unary maths for the block's norm
+};
+
+// Collapsed elementwise problem; dim 0 is the FASTEST varying dimension.  Strides in bytes.
+struct EwPlan {
+    int ndim;
+    int nin;             // number of tensor inputs (0, 1 or 2)
+    int op;
+    int acc;             // AccKind the op computes in
+    int64_t numel;
+    int64_t shape[kPlanDims];
+    int64_t stride[3][kPlanDims];  // [0] = out, [1] = a, [2] = b
+    void *ptr[3];
+    int dtype[3];
+    int b_is_scalar;     // b operand is `scalar` (already rounded through the tensor dtype)
+    double scalar;       // also the fill value
+};
+void launch_elementwise(const EwPlan &plan);
+
+// Batched tiled transpose-copy (same dtype): out is dense in the collapsed order, `in` has unit stride
+// along collapsed dim `tdim` > 0.  Both sides are moved in full 128 B lines through shared memory.
+struct TransposePlan {
+    int ndim;
+    int tdim;
+    int itemsize;
+    int64_t shape[kPlanDims];
+    int64_t in_stride[kPlanDims];   // elements
+    int64_t out_stride[kPlanDims];  // elements
+    const void *in;
+    void *out;
+};
+void launch_transpose(const TransposePlan &plan);
+
+// Single-axis reduction over a dense [outer, R, inner] input; out is [outer, inner] (keepdim handled by caller).
+// mean: result = sum * factor (factor computed by the caller in the reference's arithmetic).
+struct ReducePlan {
+    const void *in;
+    void *out;
+    int dtype;
+    int64_t outer, R, inner;
+    int is_mean;
+    double factor;
+};
+void launch_reduce(const ReducePlan &plan);
+
+// Segmented stable sort of `nseg` dense rows of length n: values + int64 indices.
+void launch_sort_rows(const void *in, void *values, int64_t *indices, int dtype, int64_t nseg, int64_t n, bool descending);
+// Row-wise top-k (sorted, ties -> lowest index first).  Returns false when the fast select path does not
+// apply (caller then falls back to sort + narrow exactly like the reference, sort_ops_kernel.cu:617-632).
+bool launch_topk_rows(const void *in, void *values, int64_t *indices, int dtype, int64_t nseg, int64_t n, int64_t k, bool largest);
+
+// index_put_ (ref: tensor_index.h:19-143): self[idx0[i], idx1[i], ...] = values[i]
+void launch_index_put(void *self, int dtype, const int64_t *self_shape, const int64_t *self_stride, int nidx, int64_t inner,
+                      const int64_t *const *idx_ptrs, const void *values, int64_t n);
+
+// GEMM: C[b][M,N] = alpha * op(A)[b][M,K] @ op(B)[b][K,N] + beta * C.  Row-major storage with leading
+// dimensions in elements; trans flag = operand is stored as [K,M] / [N,K].  batch strides in elements (0 = broadcast).
+struct GemmPlan {
+    const void *a, *b;
+    void *c;
+    int dtype;
+    int64_t M, N, K, batch;
+    int64_t lda, ldb, ldc;
+    int64_t sa, sb, sc;
+    int trans_a, trans_b;
+    float alpha, beta;
+};
+void launch_gemm_simt(const GemmPlan &p);  // fp32 / fp64 FFMA/DFMA path (strict-parity path)
+bool launch_gemm_tc(const GemmPlan &p);    // fp16 / bf16 tcgen05 + TMEM + TMA path; false if shape unsupported
+void launch_gemm(const GemmPlan &p);       // dispatcher
+
+// Causal attention (top-left aligned mask, scale 1/sqrt(D)); q [BH,Sq,D], k/v [BH,Skv,D] dense.
+struct AttnPlan {
+    const void *q, *k, *v;
+    void *out;
+    float *lse;  // [BH, Sq] natural-log LSE, may be null
+    int dtype;
+    int64_t BH, Sq, Skv, D;
+};
+void launch_attention_fwd(const AttnPlan &p);
+bool launch_attention_fwd_tc(const AttnPlan &p);
+struct AttnBwdPlan {
+    const void *q, *k, *v, *out, *dout;
+    const float *lse;
+    void *dq, *dk, *dv;
+    int dtype;
+    int64_t BH, Sq, Skv, D;
+};
+void launch_attention_bwd(const AttnBwdPlan &p);
+
+std::string device_info_string();
+
+// host-side 16-bit float helpers (RN-even, NaN-preserving), ref: src/core/include/half.h:195-208,268-290
+uint16_t f32_to_f16_bits(float f);
+uint16_t f32_to_bf16_bits(float f);
+float f16_bits_to_f32(uint16_t h);
+float bf16_bits_to_f32(uint16_t h);
+
+}  // namespace kf

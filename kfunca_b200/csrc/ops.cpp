@@ -1,0 +1,841 @@
+// Operator front-ends.  One function per reference `gpu::` entry (src/core/{binary,unary,nullary,reduce,
+// sort,gemm,nn,index}_ops.cpp, tensor_shape.cpp) with the same argument meaning and error conditions,
+// plus the GradFunctions the reference never wrote (only AddGradFunction exists there,
+// src/core/binary_ops.cpp:16-43) so that the transformer block can run backward.
+#include "ops.h"
+
+#include <algorithm>
+#include <cmath>
+#include <queue>
+#include <unordered_map>
+
+#include "runtime.h"
+
+namespace kf {
+namespace ops {
+
+static void require_device(const Tensor &t, const char *what) {
+    KF_CHECK(t.defined(), what, ": undefined tensor");
+    KF_CHECK(!t.is_meta(), what, ": meta tensors carry no data (kfunca_b200 has no CPU compute path)");
+}
+
+static bool any_requires_grad(std::initializer_list<const Tensor *> ts) {
+    for (auto *t : ts)
+        if (t && t->defined() && t->requires_grad()) return true;
+    return false;
+}
+template <class F>
+static void attach(Tensor &out, F *fn, std::initializer_list<Tensor> inputs) {
+    for (auto &t : inputs) fn->inputs.push_back(t);
+    out.impl->requires_grad = true;
+    out.grad_fn = Ref<GradFunction>(fn);
+}
+
+// scalar -> acc_t -> dtype -> acc_t on the host (what the reference gets by filling a tensor, register.cpp:172-206)
+static double round_scalar_through(DType dt, double v) {
+    switch (dt) {
+    case KF_DOUBLE: return v;
+    case KF_FLOAT: return (double)(float)v;
+    case KF_HALF: return (double)f16_bits_to_f32(f32_to_f16_bits((float)v));
+    case KF_BFLOAT16: return (double)bf16_bits_to_f32(f32_to_bf16_bits((float)v));
+    case KF_BOOL: return v != 0.0 ? 1.0 : 0.0;
+    case KF_BYTE: return (double)(uint8_t)(int64_t)v;
+    case KF_CHAR: return (double)(int8_t)(int64_t)v;
+    case KF_SHORT: return (double)(int16_t)(int64_t)v;
+    case KF_INT: return (double)(int32_t)(int64_t)v;
+    default: return (double)(int64_t)v;
+    }
+}
+
+// ================================================================== elementwise
+static void run_binary(int op, Tensor &out, const Tensor &a, const Tensor &b) {
+    require_device(a, "binary op");
+    require_device(b, "binary op");
+    EwPlan plan;
+    plan_elementwise(plan, out, &a, &b, true);
+    plan.op = op;
+    launch_elementwise(plan);
+}
+
+struct BinaryGrad : GradFunction {
+    int op;
+    Tensor a, b;  // detached saved operands (mul/div)
+    std::vector<int64_t> sa, sb;
+    const char *name() const override { return "BinaryGrad"; }
+    std::vector<Tensor> backward(const Tensor &g) override {
+        std::vector<Tensor> r(2);
+        const bool na = inputs[0].requires_grad(), nb = inputs[1].requires_grad();
+        switch (op) {
+        case EW_ADD:
+            if (na) r[0] = sum_to_shape(g, sa);
+            if (nb) r[1] = sum_to_shape(g, sb);
+            break;
+        case EW_SUB:
+            if (na) r[0] = sum_to_shape(g, sa);
+            if (nb) r[1] = sum_to_shape(unary(EW_NEG, g), sb);
+            break;
+        case EW_MUL:
+            if (na) r[0] = sum_to_shape(binary(EW_MUL, g, b), sa);
+            if (nb) r[1] = sum_to_shape(binary(EW_MUL, g, a), sb);
+            break;
+        default: {  // a / b
+            Tensor gq = binary(EW_DIV, g, b);
+            if (na) r[0] = sum_to_shape(gq, sa);
+            if (nb) r[1] = sum_to_shape(unary(EW_NEG, binary(EW_MUL, gq, binary(EW_DIV, a, b))), sb);
+        }
+        }
+        return r;
+    }
+};
+
+Tensor binary(int op, const Tensor &a, const Tensor &b) {
+    Tensor out;
+    run_binary(op, out, a, b);
+    if (any_requires_grad({&a, &b})) {
+        auto *fn = new BinaryGrad();
+        fn->op = op;
+        fn->sa = a.sizes();
+        fn->sb = b.sizes();
+        if (op == EW_MUL || op == EW_DIV) {
+            fn->a = a.detach();
+            fn->b = b.detach();
+        }
+        attach(out, fn, {a, b});
+    }
+    return out;
+}
+
+Tensor &binary_(int op, Tensor &self, const Tensor &other) {
+    run_binary(op, self, self, other);
+    return self;
+}
+
+static void run_binary_scalar(int op, Tensor &out, const Tensor &a, double scalar) {
+    require_device(a, "binary op");
+    EwPlan plan;
+    plan_elementwise(plan, out, &a, nullptr, true);
+    plan.op = op;
+    plan.nin = 2;
+    plan.b_is_scalar = 1;
+    plan.scalar = round_scalar_through(a.dtype(), scalar);
+    launch_elementwise(plan);
+}
+
+struct ScalarGrad : GradFunction {
+    int op;
+    double s;
+    const char *name() const override { return "ScalarGrad"; }
+    std::vector<Tensor> backward(const Tensor &g) override {
+        if (op == EW_MUL || op == EW_DIV) return {binary_scalar(op, g, s)};
+        return {g};
+    }
+};
+
+Tensor binary_scalar(int op, const Tensor &a, double scalar) {
+    Tensor out;
+    run_binary_scalar(op, out, a, scalar);
+    if (a.requires_grad()) {
+        auto *fn = new ScalarGrad();
+        fn->op = op;
+        fn->s = scalar;
+        attach(out, fn, {a});
+    }
+    return out;
+}
+Tensor &binary_scalar_(int op, Tensor &self, double scalar) {
+    run_binary_scalar(op, self, self, scalar);
+    return self;
+}
+
+Tensor &fill_(Tensor &self, double value) {
+    require_device(self, "fill_");
+    EwPlan plan;
+    plan_elementwise(plan, self, nullptr, nullptr, false);
+    plan.op = EW_FILL;
+    plan.acc = acc_kind(self.dtype());
+    plan.scalar = value;
+    launch_elementwise(plan);
+    return self;
+}
+
+// copy with optional dtype cast; picks the tiled transpose when the layouts call for it
+static void run_copy(Tensor &dst, const Tensor &src) {
+    require_device(dst, "copy_");
+    require_device(src, "copy_");
+    EwPlan plan;
+    Tensor d = dst;
+    plan_elementwise(plan, d, &src, nullptr, false);
+    plan.op = EW_COPY;
+    plan.acc = acc_kind(dst.dtype());
+    if (plan.numel == 0) return;
+    const int64_t isz = (int64_t)dst.itemsize();
+    if (dst.dtype() == src.dtype() && plan.ndim >= 2 && plan.stride[0][0] == isz && plan.stride[1][0] != isz) {
+        int tdim = -1;
+        for (int dd = 1; dd < plan.ndim; ++dd)
+            if (plan.stride[1][dd] == isz) tdim = dd;
+        bool ok = tdim > 0 && plan.shape[0] >= 8 && plan.shape[tdim] >= 8;
+        for (int dd = 0; dd < plan.ndim && ok; ++dd)
+            if (plan.stride[0][dd] % isz || plan.stride[1][dd] % isz || plan.stride[0][dd] < 0 || plan.stride[1][dd] < 0) ok = false;
+        if (ok) {
+            TransposePlan tp{};
+            tp.ndim = plan.ndim;
+            tp.tdim = tdim;
+            tp.itemsize = (int)isz;
+            for (int dd = 0; dd < plan.ndim; ++dd) {
+                tp.shape[dd] = plan.shape[dd];
+                tp.out_stride[dd] = plan.stride[0][dd] / isz;
+                tp.in_stride[dd] = plan.stride[1][dd] / isz;
+            }
+            tp.in = plan.ptr[1];
+            tp.out = plan.ptr[0];
+            launch_transpose(tp);
+            return;
+        }
+    }
+    launch_elementwise(plan);
+}
+
+Tensor &copy_(Tensor &self, const Tensor &src) {
+    run_copy(self, src);
+    return self;
+}
+
+struct IdentityGrad : GradFunction {  // clone / contiguous
+    const char *name() const override { return "IdentityGrad"; }
+    std::vector<Tensor> backward(const Tensor &g) override { return {g}; }
+};
+
+Tensor clone(const Tensor &self) {
+    Tensor out = empty_like(self);
+    run_copy(out, self);
+    if (self.requires_grad()) attach(out, new IdentityGrad(), {self});
+    return out;
+}
+Tensor contiguous(const Tensor &self) {
+    if (self.is_contiguous()) return self;
+    return clone(self);
+}
+
+struct ConvertGrad : GradFunction {
+    DType src;
+    const char *name() const override { return "ConvertGrad"; }
+    std::vector<Tensor> backward(const Tensor &g) override { return {convert(g, src)}; }
+};
+Tensor convert(const Tensor &self, DType dtype) {
+    require_device(self, "convert");
+    Tensor out = empty(self.sizes(), dtype, self.device());
+    run_copy(out, self);
+    if (self.requires_grad() && is_floating(dtype)) {
+        auto *fn = new ConvertGrad();
+        fn->src = self.dtype();
+        attach(out, fn, {self});
+    }
+    return out;
+}
+
+struct UnaryGrad : GradFunction {
+    int op;
+    Tensor y;  // saved output
+    const char *name() const override { return "UnaryGrad"; }
+    std::vector<Tensor> backward(const Tensor &g) override {
+        if (op == EW_NEG) return {unary(EW_NEG, g)};
+        if (op == EW_SQRT) return {binary(EW_DIV, binary_scalar(EW_MUL, g, 0.5), y)};  // g / (2 sqrt(x))
+        // rsqrt: d/dx x^-1/2 = -1/2 y^3
+        return {binary_scalar(EW_MUL, binary(EW_MUL, g, binary(EW_MUL, y, binary(EW_MUL, y, y))), -0.5)};
+    }
+};
+Tensor unary(int op, const Tensor &a) {
+    require_device(a, "unary op");
+    Tensor out;
+    EwPlan plan;
+    plan_elementwise(plan, out, &a, nullptr, true);
+    plan.op = op;
+    launch_elementwise(plan);
+    if (a.requires_grad()) {
+        auto *fn = new UnaryGrad();
+        fn->op = op;
+        fn->y = out.detach();
+        attach(out, fn, {a});
+    }
+    return out;
+}
+
+// ================================================================== reductions
+struct ReduceGrad : GradFunction {
+    std::vector<int64_t> in_shape;
+    bool is_mean;
+    int64_t R;
+    const char *name() const override { return "ReduceGrad"; }
+    std::vector<Tensor> backward(const Tensor &g) override {
+        Tensor gi = empty(in_shape, g.dtype(), g.device());
+        Tensor src = is_mean ? binary_scalar(EW_MUL, g, 1.0 / (double)R) : g;
+        run_copy(gi, src);  // broadcast along the reduced dim
+        return {gi};
+    }
+};
+
+static Tensor reduce_impl(const Tensor &self, int64_t dim_, bool is_mean) {
+    require_device(self, "reduce");
+    const int d = wrap_dim(dim_, self.dim());
+    Tensor x = self.is_contiguous() ? self : clone(self.detach());
+    auto out_shape = self.sizes();
+    out_shape[d] = 1;
+    Tensor out = empty(out_shape, self.dtype(), self.device());
+    ReducePlan p{};
+    p.in = x.data();
+    p.out = out.data();
+    p.dtype = self.dtype();
+    p.outer = 1;
+    p.inner = 1;
+    for (int i = 0; i < d; ++i) p.outer *= self.size(i);
+    for (int i = d + 1; i < self.dim(); ++i) p.inner *= self.size(i);
+    p.R = self.size(d);
+    p.is_mean = is_mean;
+    const int64_t n_out = p.outer * p.inner, numel = self.numel();
+    if (is_mean) {
+        // ref: factor = static_cast<acc_t>(num_output_elements) / numel in the tensor's own arithmetic
+        // (reduce_ops_kernel.cu:49-53): integer dtypes integer-divide; 16-bit floats use fp32 here (deviation).
+        switch (self.dtype()) {
+        case KF_DOUBLE: p.factor = numel ? (double)n_out / (double)numel : 0.0; break;
+        case KF_FLOAT: case KF_HALF: case KF_BFLOAT16: p.factor = numel ? (double)((float)n_out / (float)numel) : 0.0; break;
+        case KF_BOOL: p.factor = (numel && ((n_out != 0 ? 1 : 0) / numel) != 0) ? 1.0 : 0.0; break;
+        case KF_BYTE: p.factor = numel ? (double)(uint8_t)((int64_t)(uint8_t)n_out / numel) : 0.0; break;
+        case KF_CHAR: p.factor = numel ? (double)(int8_t)((int64_t)(int8_t)n_out / numel) : 0.0; break;
+        case KF_SHORT: p.factor = numel ? (double)(int16_t)((int64_t)(int16_t)n_out / numel) : 0.0; break;
+        case KF_INT: p.factor = numel ? (double)(int32_t)((int64_t)(int32_t)n_out / numel) : 0.0; break;
+        default: p.factor = numel ? (double)(n_out / numel) : 0.0; break;
+        }
+    }
+    if (p.R == 0) {
+        fill_(out, 0.0);
+    } else {
+        launch_reduce(p);
+    }
+    if (self.requires_grad()) {
+        auto *fn = new ReduceGrad();
+        fn->in_shape = self.sizes();
+        fn->is_mean = is_mean;
+        fn->R = p.R;
+        attach(out, fn, {self});
+    }
+    return out;
+}
+Tensor sum(const Tensor &self, int64_t dim) { return reduce_impl(self, dim, false); }
+Tensor mean(const Tensor &self, int64_t dim) { return reduce_impl(self, dim, true); }
+
+Tensor sum_to_shape(const Tensor &grad, const std::vector<int64_t> &shape) {
+    Tensor g = grad;
+    KF_CHECK((int)shape.size() == g.dim());
+    for (int d = 0; d < g.dim(); ++d)
+        if (shape[d] == 1 && g.size(d) != 1) g = sum(g.detach(), d);
+    return g;
+}
+
+std::tuple<Tensor, Tensor> mean_var(const Tensor &self, int64_t dim, bool take_sqrt) {
+    // ref: gpu::mean_var (reduce_ops.cpp:22-28) = Welford with correction 1; fp32/fp64 only (DISPATCH_FLOATING_TYPES)
+    KF_CHECK(self.dtype() == KF_FLOAT || self.dtype() == KF_DOUBLE, "Unsupported ScalarType ", dtype_name(self.dtype()));
+    const int d = wrap_dim(dim, self.dim());
+    Tensor x = self.detach();
+    Tensor m = mean(x, d);
+    Tensor diff = binary(EW_SUB, x, m);
+    Tensor m2 = sum(binary(EW_MUL, diff, diff), d);
+    const double div = (double)self.size(d) - 1.0;
+    Tensor var = binary_scalar(EW_DIV, m2, div > 0 ? div : 0.0);
+    if (take_sqrt) var = unary(EW_SQRT, var);
+    return {m, var};
+}
+
+std::tuple<Tensor, Tensor> norm_stat(const Tensor &self, int64_t dim) {
+    // ref: norm_stat_kernel (src/device/norm_ops_kernel.cu:6-61): 2-D, dim 0, biased variance, eps 1e-12
+    KF_CHECK(self.defined());
+    KF_CHECK(dim == 0 && self.dim() == 2);
+    KF_CHECK(self.dtype() == KF_FLOAT || self.dtype() == KF_DOUBLE, "Unsupported ScalarType ", dtype_name(self.dtype()));
+    Tensor x = self.detach();
+    Tensor m = mean(x, 0);
+    Tensor diff = binary(EW_SUB, x, m);
+    Tensor var = mean(binary(EW_MUL, diff, diff), 0);
+    Tensor invstd = unary(EW_RSQRT, binary_scalar(EW_ADD, var, 1e-12));
+    return {m, invstd};
+}
+
+// ================================================================== sort / top-k
+static Tensor move_dim_last(const Tensor &t, int d) {
+    std::vector<int64_t> perm;
+    for (int i = 0; i < t.dim(); ++i)
+        if (i != d) perm.push_back(i);
+    perm.push_back(d);
+    return t.permute(perm);
+}
+static Tensor move_last_to(const Tensor &t, int d) {
+    std::vector<int64_t> perm(t.dim());
+    int src = 0;
+    for (int i = 0; i < t.dim(); ++i) perm[i] = (i == d) ? t.dim() - 1 : src++;
+    return t.permute(perm);
+}
+
+std::tuple<Tensor, Tensor> sort(const Tensor &self, int64_t dim_, bool descending) {
+    require_device(self, "sort");
+    const int d = wrap_dim(dim_, self.dim());
+    KF_CHECK(self.dtype() != KF_BOOL, "Sort currently does not support bool dtypes.");
+    const int64_t n = self.size(d);
+    KF_CHECK(n <= 0x7FFFFFFF, "The dimension being sorted can not have more than INT_MAX elements.");
+    Tensor rows = move_dim_last(self.detach(), d).contiguous();
+    Tensor vals = empty(rows.sizes(), self.dtype(), self.device());
+    Tensor idx = empty(rows.sizes(), KF_LONG, self.device());
+    if (self.numel() > 0) launch_sort_rows(rows.data(), vals.data(), idx.data_as<int64_t>(), self.dtype(), self.numel() / n, n, descending);
+    if (d == self.dim() - 1) return {vals, idx};
+    return {move_last_to(vals, d).contiguous(), move_last_to(idx, d).contiguous()};
+}
+
+std::tuple<Tensor, Tensor> topk(const Tensor &self, int64_t k, int64_t dim_, bool largest) {
+    require_device(self, "topk");
+    const int d = wrap_dim(dim_, self.dim());
+    KF_CHECK(self.dtype() != KF_BOOL, "Sort currently does not support bool dtypes.");
+    const int64_t n = self.size(d);
+    KF_CHECK(k >= 0 && k <= n, "start (0) + length (", k, ") exceeds dimension size (", n, ").");
+    Tensor rows = move_dim_last(self.detach(), d).contiguous();
+    auto out_shape = rows.sizes();
+    out_shape.back() = k;
+    Tensor vals = empty(out_shape, self.dtype(), self.device());
+    Tensor idx = empty(out_shape, KF_LONG, self.device());
+    const int64_t nseg = n ? self.numel() / n : 0;
+    if (nseg > 0 && k > 0) {
+        if (!launch_topk_rows(rows.data(), vals.data(), idx.data_as<int64_t>(), self.dtype(), nseg, n, k, largest)) {
+            // reference algorithm: full stable sort, keep the first k (sort_ops_kernel.cu:617-632)
+            Tensor sv = empty(rows.sizes(), self.dtype(), self.device());
+            Tensor si = empty(rows.sizes(), KF_LONG, self.device());
+            launch_sort_rows(rows.data(), sv.data(), si.data_as<int64_t>(), self.dtype(), nseg, n, largest);
+            run_copy(vals, sv.narrow(-1, 0, k));
+            run_copy(idx, si.narrow(-1, 0, k));
+        }
+    }
+    if (d == self.dim() - 1) return {vals, idx};
+    return {move_last_to(vals, d).contiguous(), move_last_to(idx, d).contiguous()};
+}
+
+// ================================================================== shape ops
+struct CatGrad : GradFunction {
+    int dim;
+    std::vector<int64_t> sizes;
+    const char *name() const override { return "CatGrad"; }
+    std::vector<Tensor> backward(const Tensor &g) override {
+        std::vector<Tensor> r;
+        int64_t off = 0;
+        for (auto s : sizes) {
+            r.push_back(g.narrow(dim, off, s));
+            off += s;
+        }
+        return r;
+    }
+};
+
+Tensor cat(const std::vector<Tensor> &tensors, int64_t dim_) {
+    KF_CHECK(!tensors.empty(), "cat(): empty tensor list");
+    const Tensor &first = tensors[0];
+    require_device(first, "cat");
+    const int d = wrap_dim(dim_, first.dim());
+    int64_t total = first.size(d);
+    bool rg = first.requires_grad();
+    for (size_t i = 1; i < tensors.size(); ++i) {
+        const Tensor &t = tensors[i];
+        KF_CHECK(first.device() == t.device());
+        KF_CHECK(first.dim() == t.dim(), "Tensors must have same number of dimensions: got ", first.dim(), " and ", t.dim());
+        for (int k = 0; k < first.dim(); ++k) {
+            if (k == d) continue;
+            KF_CHECK(first.size(k) == t.size(k), "Sizes of tensors must match except in dimension ", d, ". Expected size ",
+                     first.size(k), " but got size ", t.size(k), " for tensor number ", i, " in the list.");
+        }
+        total += t.size(d);
+        rg = rg || t.requires_grad();
+    }
+    auto out_shape = first.sizes();
+    out_shape[d] = total;
+    Tensor out = empty(out_shape, first.dtype(), first.device());
+    int64_t off = 0;
+    for (const Tensor &t : tensors) {
+        Tensor nt = out.narrow(d, off, t.size(d));
+        run_copy(nt, t);
+        off += t.size(d);
+    }
+    if (rg) {
+        auto *fn = new CatGrad();
+        fn->dim = d;
+        for (auto &t : tensors) {
+            fn->sizes.push_back(t.size(d));
+            fn->inputs.push_back(t);
+        }
+        out.impl->requires_grad = true;
+        out.grad_fn = Ref<GradFunction>(fn);
+    }
+    return out;
+}
+
+struct SliceGrad : GradFunction {
+    std::vector<int64_t> in_shape;
+    int64_t dim, start, end, step;
+    const char *name() const override { return "SliceGrad"; }
+    std::vector<Tensor> backward(const Tensor &g) override {
+        Tensor gi = zeros(in_shape, g.dtype(), g.device());
+        Tensor dst = gi.slice(dim, start, end, step);
+        run_copy(dst, g);
+        return {gi};
+    }
+};
+Tensor slice(const Tensor &self, int64_t dim, int64_t start, int64_t end, int64_t step) {
+    Tensor out = self.slice(dim, start, end, step);
+    if (self.requires_grad()) {
+        auto *fn = new SliceGrad();
+        fn->in_shape = self.sizes();
+        fn->dim = dim; fn->start = start; fn->end = end; fn->step = step;
+        attach(out, fn, {self});
+    }
+    return out;
+}
+
+std::vector<Tensor> split(const Tensor &self, const std::vector<int64_t> &sizes, int64_t dim_) {
+    KF_CHECK(self.dim() > 0, "tensor_split expected at least a 1-dimensional tensor, but got a tensor with ", self.dim(), " dims");
+    const int d = wrap_dim(dim_, self.dim());
+    std::vector<Tensor> out;
+    int64_t start = 0;
+    for (auto s : sizes) {
+        out.push_back(slice(self, d, start, start + s, 1));
+        start += s;
+    }
+    KF_CHECK(start == self.size(d), "split sizes must sum to the dimension size");
+    return out;
+}
+
+struct PermuteGrad : GradFunction {
+    std::vector<int64_t> inv;
+    const char *name() const override { return "PermuteGrad"; }
+    std::vector<Tensor> backward(const Tensor &g) override { return {g.permute(inv)}; }
+};
+Tensor permute(const Tensor &self, const std::vector<int64_t> &dims) {
+    Tensor out = self.permute(dims);
+    if (self.requires_grad()) {
+        auto *fn = new PermuteGrad();
+        fn->inv.resize(dims.size());
+        for (size_t i = 0; i < dims.size(); ++i) fn->inv[wrap_dim(dims[i], (int64_t)dims.size())] = (int64_t)i;
+        attach(out, fn, {self});
+    }
+    return out;
+}
+struct ViewGrad : GradFunction {
+    std::vector<int64_t> in_shape;
+    const char *name() const override { return "ViewGrad"; }
+    std::vector<Tensor> backward(const Tensor &g) override { return {g.contiguous().view(in_shape)}; }
+};
+Tensor view(const Tensor &self, const std::vector<int64_t> &sizes) {
+    Tensor out = self.view(sizes);
+    if (self.requires_grad()) {
+        auto *fn = new ViewGrad();
+        fn->in_shape = self.sizes();
+        attach(out, fn, {self});
+    }
+    return out;
+}
+
+Tensor &index_put_(Tensor &self, const std::vector<Tensor> &indices, const Tensor &values) {
+    KF_CHECK((int)indices.size() == self.dim(), "Number of indices must match the number of dimensions in the tensor.");
+    KF_CHECK(self.defined() && values.defined(), "Both self and values tensors must be defined.");
+    KF_CHECK(self.dtype() == values.dtype(), "Data types of self and values tensors must match.");
+    require_device(self, "index_put_");
+    const int64_t n = values.numel();
+    std::vector<Tensor> keep;
+    std::vector<const int64_t *> ptrs;
+    for (auto &ix : indices) {
+        KF_CHECK(ix.defined() && ix.dtype() == KF_LONG, "Indices must be of type Long.");
+        KF_CHECK(ix.numel() == n, "indices and values must have the same number of elements");
+        keep.push_back(ix.contiguous());
+        ptrs.push_back(keep.back().data_as<int64_t>());
+    }
+    for (int d = 0; d < self.dim(); ++d) KF_CHECK(self.size(d) != 0, "index is out of bounds for dimension with size 0");
+    Tensor v = values.contiguous();
+    auto sizes = self.sizes(), strides = self.strides();
+    launch_index_put(self.data(), self.dtype(), sizes.data(), strides.data(), self.dim(), 1, ptrs.data(), v.data(), n);
+    return self;
+}
+
+// ================================================================== GEMM
+static void fill_gemm_operand(const Tensor &t, bool trans, int64_t &rows, int64_t &cols, int64_t &ld, int64_t &bstride, int64_t &batch,
+                              Tensor &holder) {
+    // accept [.., r, c] with unit stride on the last dim and a uniform batch stride; anything else is materialised
+    holder = t;
+    auto ok = [&](const Tensor &x) {
+        if (x.dim() < 2 || x.stride(-1) != 1) return false;
+        if (x.size(-2) > 1 && x.stride(-2) < x.size(-1)) return false;
+        int64_t expect = -1;
+        for (int i = x.dim() - 3; i >= 0; --i) {  // leading dims must form one dense batch index
+            if (x.size(i) == 1) continue;
+            if (expect < 0) expect = x.stride(i) * x.size(i);
+            else {
+                if (x.stride(i) != expect) return false;
+                expect = x.stride(i) * x.size(i);
+            }
+        }
+        return true;
+    };
+    if (!ok(holder)) holder = clone(holder.detach());
+    const Tensor &x = holder;
+    batch = 1;
+    for (int i = 0; i < x.dim() - 2; ++i) batch *= x.size(i);
+    bstride = 0;
+    for (int i = x.dim() - 3; i >= 0; --i)
+        if (x.size(i) != 1) { bstride = x.stride(i); break; }
+    if (batch == 1) bstride = 0;
+    ld = x.size(-2) > 1 ? x.stride(-2) : x.size(-1);
+    rows = trans ? x.size(-1) : x.size(-2);
+    cols = trans ? x.size(-2) : x.size(-1);
+}
+
+struct MatmulGrad : GradFunction {
+    Tensor a, b;
+    bool ta, tb;
+    float alpha;
+    bool b_shared;  // b was 2-D against a batched a (gemm semantics)
+    const char *name() const override { return "MatmulGrad"; }
+    std::vector<Tensor> backward(const Tensor &g) override;
+};
+
+static Tensor matmul_nograd(const Tensor &a, bool ta, const Tensor &b, bool tb, float alpha, float beta, Tensor *out_opt) {
+    require_device(a, "matmul");
+    require_device(b, "matmul");
+    KF_CHECK(a.dtype() == b.dtype(), "matmul: dtype mismatch");
+    KF_CHECK(a.dim() >= 2 && b.dim() >= 2, "matmul needs >= 2-d operands");
+    Tensor ha, hb;
+    GemmPlan p{};
+    int64_t Ka, Kb, batch_a, batch_b;
+    fill_gemm_operand(a, ta, p.M, Ka, p.lda, p.sa, batch_a, ha);
+    fill_gemm_operand(b, tb, Kb, p.N, p.ldb, p.sb, batch_b, hb);
+    KF_CHECK(Ka == Kb, "matmul: inner dimensions differ (", Ka, " vs ", Kb, ")");
+    p.K = Ka;
+    std::vector<int64_t> out_shape;
+    if (b.dim() == 2 && !ta && a.dim() > 2 && ha.is_contiguous()) {
+        // gemm semantics: fold every leading dim of a into M (ref: gemm_kernel.cu:10-15)
+        p.M *= batch_a;
+        batch_a = 1;
+        p.sa = 0;
+        out_shape = a.sizes();
+        out_shape.back() = p.N;
+    } else {
+        KF_CHECK(batch_a == batch_b || batch_a == 1 || batch_b == 1, "matmul: batch dims differ");
+        const Tensor &lead = batch_a >= batch_b ? a : b;
+        for (int i = 0; i < lead.dim() - 2; ++i) out_shape.push_back(lead.size(i));
+        out_shape.push_back(p.M);
+        out_shape.push_back(p.N);
+    }
+    p.batch = std::max(batch_a, batch_b);
+    if (batch_a == 1) p.sa = 0;
+    if (batch_b == 1) p.sb = 0;
+    Tensor out;
+    if (out_opt) {
+        out = *out_opt;
+        KF_CHECK(out.is_contiguous() && out.dtype() == a.dtype());
+        KF_CHECK(out.numel() == p.batch * p.M * p.N, "gemm_out: output has the wrong number of elements");
+    } else {
+        out = empty(out_shape, a.dtype(), a.device());
+    }
+    p.a = ha.data();
+    p.b = hb.data();
+    p.c = out.data();
+    p.dtype = a.dtype();
+    p.ldc = p.N;
+    p.sc = p.M * p.N;
+    p.trans_a = ta;
+    p.trans_b = tb;
+    p.alpha = alpha;
+    p.beta = beta;
+    if (out.numel() > 0) launch_gemm(p);
+    return out;
+}
+
+std::vector<Tensor> MatmulGrad::backward(const Tensor &g0) {
+    std::vector<Tensor> r(2);
+    Tensor g = g0.contiguous();
+    const bool na = inputs[0].requires_grad(), nb = inputs[1].requires_grad();
+    Tensor g2 = g, a2 = a;
+    if (b_shared) {  // fold the leading dims like the forward did
+        g2 = g.view({-1, g.size(-1)});
+        a2 = a.contiguous().view({-1, a.size(-1)});
+    }
+    if (na) {
+        // C = op(A) op(B): dA = dC op(B)^T (or its transpose when A was transposed)
+        Tensor da = ta ? matmul_nograd(b, tb, g2, true, alpha, 0.f, nullptr) : matmul_nograd(g2, false, b, !tb, alpha, 0.f, nullptr);
+        r[0] = b_shared ? da.view(a.sizes()) : da;
+    }
+    if (nb) {
+        Tensor db = tb ? matmul_nograd(g2, true, a2, ta, alpha, 0.f, nullptr) : matmul_nograd(a2, !ta, g2, false, alpha, 0.f, nullptr);
+        r[1] = db;
+    }
+    return r;
+}
+
+Tensor matmul(const Tensor &a, bool ta, const Tensor &b, bool tb, float alpha) {
+    Tensor out = matmul_nograd(a, ta, b, tb, alpha, 0.f, nullptr);
+    if (any_requires_grad({&a, &b})) {
+        auto *fn = new MatmulGrad();
+        fn->a = a.detach();
+        fn->b = b.detach();
+        fn->ta = ta;
+        fn->tb = tb;
+        fn->alpha = alpha;
+        fn->b_shared = (b.dim() == 2 && !ta && a.dim() > 2);
+        attach(out, fn, {a, b});
+    }
+    return out;
+}
+
+Tensor gemm(const Tensor &a, const Tensor &b, float alpha, float beta) {
+    // ref: gpu::gemm (src/core/gemm_ops.cpp:10-16) + checks of gemm_kernel (src/device/gemm_kernel.cu:8-25).
+    // The reference hands CUTLASS an uninitialised `out`, so beta != 0 reads garbage there; we define it as beta*0.
+    KF_CHECK(a.is_contiguous() && b.is_contiguous(), "gemm: operands must be contiguous");
+    KF_CHECK(b.dim() == 2 && b.size(0) == a.size(-1), "gemm: b must be [K, N]");
+    KF_CHECK(a.dtype() == b.dtype(), "gemm: dtype mismatch");
+    (void)beta;
+    if (a.dim() == 1) {
+        Tensor a2 = view(a, {1, a.size(0)});
+        Tensor o = matmul(a2, false, b, false, alpha);
+        return view(o, {b.size(1)});
+    }
+    return matmul(a, false, b, false, alpha);
+}
+
+void gemm_out(Tensor &out, const Tensor &a, const Tensor &b, float alpha, float beta) {
+    KF_CHECK(out.is_contiguous() && a.is_contiguous() && b.is_contiguous());
+    KF_CHECK(b.dim() == 2 && b.size(0) == a.size(-1));
+    KF_CHECK(a.dtype() == b.dtype());
+    KF_CHECK(out.size(-1) == b.size(-1));
+    Tensor a2 = a.dim() == 1 ? a.view({1, a.size(0)}) : a;
+    matmul_nograd(a2, false, b, false, alpha, beta, &out);
+}
+
+// ================================================================== attention
+struct AttentionGrad : GradFunction {
+    Tensor q, k, v, out, lse;
+    const char *name() const override { return "AttentionGrad"; }
+    std::vector<Tensor> backward(const Tensor &g) override {
+        auto [dq, dk, dv] = causal_attention_bwd(g, q, k, v, out, lse);
+        return {dq, dk, dv};
+    }
+};
+
+static void check_attention(const Tensor &q, const Tensor &k, const Tensor &v) {
+    require_device(q, "causal_attention");
+    require_device(k, "causal_attention");
+    require_device(v, "causal_attention");
+    KF_CHECK(q.dim() == 4 && k.dim() == 4 && v.dim() == 4, "causal_attention expects [B, H, S, D] tensors");
+    KF_CHECK(k.size(0) == q.size(0) && k.size(1) == q.size(1) && k.size(3) == q.size(3));
+    KF_CHECK(k.sizes() == v.sizes());
+    KF_CHECK(q.dtype() == k.dtype() && q.dtype() == v.dtype());
+    KF_CHECK(is_floating(q.dtype()), "Unsupported ScalarType ", dtype_name(q.dtype()));
+}
+
+std::tuple<Tensor, Tensor> causal_attention_fwd(const Tensor &q_, const Tensor &k_, const Tensor &v_) {
+    check_attention(q_, k_, v_);
+    Tensor q = q_.detach().contiguous(), k = k_.detach().contiguous(), v = v_.detach().contiguous();
+    Tensor out = empty(q.sizes(), q.dtype(), q.device());
+    Tensor lse = empty({q.size(0), q.size(1), q.size(2)}, KF_FLOAT, q.device());
+    AttnPlan p{};
+    p.q = q.data(); p.k = k.data(); p.v = v.data(); p.out = out.data();
+    p.lse = lse.data_as<float>();
+    p.dtype = q.dtype();
+    p.BH = q.size(0) * q.size(1);
+    p.Sq = q.size(2);
+    p.Skv = k.size(2);
+    p.D = q.size(3);
+    if (out.numel() > 0) launch_attention_fwd(p);
+    return {out, lse};
+}
+
+Tensor causal_attention(const Tensor &q, const Tensor &k, const Tensor &v) {
+    auto [out, lse] = causal_attention_fwd(q, k, v);
+    if (any_requires_grad({&q, &k, &v})) {
+        auto *fn = new AttentionGrad();
+        fn->q = q.detach().contiguous();
+        fn->k = k.detach().contiguous();
+        fn->v = v.detach().contiguous();
+        fn->out = out.detach();
+        fn->lse = lse;
+        attach(out, fn, {q, k, v});
+    }
+    return out;
+}
+
+std::tuple<Tensor, Tensor, Tensor> causal_attention_bwd(const Tensor &dout_, const Tensor &q_, const Tensor &k_, const Tensor &v_,
+                                                        const Tensor &out_, const Tensor &lse_) {
+    check_attention(q_, k_, v_);
+    Tensor q = q_.detach().contiguous(), k = k_.detach().contiguous(), v = v_.detach().contiguous();
+    Tensor o = out_.detach().contiguous(), dout = dout_.detach().contiguous(), lse = lse_.detach().contiguous();
+    KF_CHECK(dout.sizes() == q.sizes() && o.sizes() == q.sizes() && dout.dtype() == q.dtype());
+    KF_CHECK(lse.dtype() == KF_FLOAT && lse.numel() == q.size(0) * q.size(1) * q.size(2));
+    Tensor dq = empty(q.sizes(), q.dtype(), q.device());
+    Tensor dk = empty(k.sizes(), k.dtype(), k.device());
+    Tensor dv = empty(v.sizes(), v.dtype(), v.device());
+    AttnBwdPlan p{};
+    p.q = q.data(); p.k = k.data(); p.v = v.data(); p.out = o.data(); p.dout = dout.data();
+    p.lse = lse.data_as<float>();
+    p.dq = dq.data(); p.dk = dk.data(); p.dv = dv.data();
+    p.dtype = q.dtype();
+    p.BH = q.size(0) * q.size(1);
+    p.Sq = q.size(2);
+    p.Skv = k.size(2);
+    p.D = q.size(3);
+    if (q.numel() > 0) launch_attention_bwd(p);
+    return {dq, dk, dv};
+}
+
+// ================================================================== autograd engine
+// Same two-pass scheme as the reference (src/core/tensor.cpp:86-126): count consumers, then a ready
+// queue; leaf grads accumulate across backward() calls (tensor.cpp:75-84).
+void backward(Tensor &root, const Tensor &grad_output) {
+    KF_CHECK(root.defined() && grad_output.defined());
+    std::unordered_map<TensorImpl *, int> needed;
+    std::unordered_map<TensorImpl *, Tensor> grad_acc;
+    std::unordered_map<TensorImpl *, bool> visited;
+    std::queue<Tensor *> ready;
+    ready.push(&root);
+    while (!ready.empty()) {
+        Tensor *t = ready.front();
+        ready.pop();
+        if (!t->grad_fn) continue;
+        if (visited[t->impl.get()]) continue;  // expand each node once, count every edge
+        visited[t->impl.get()] = true;
+        for (auto &in : t->grad_fn->inputs) {
+            if (!in.requires_grad()) continue;
+            needed[in.impl.get()] += 1;
+            ready.push(&in);
+        }
+    }
+    grad_acc[root.impl.get()] = grad_output;
+    ready.push(&root);
+    while (!ready.empty()) {
+        Tensor *t = ready.front();
+        ready.pop();
+        Tensor go = grad_acc[t->impl.get()];
+        grad_acc.erase(t->impl.get());
+        if (t->grad_fn) {
+            auto gis = t->grad_fn->backward(go);
+            auto &inputs = t->grad_fn->inputs;
+            for (size_t i = 0; i < inputs.size(); ++i) {
+                if (!inputs[i].requires_grad()) continue;
+                KF_CHECK(i < gis.size() && gis[i].defined(), t->grad_fn->name(), " produced no gradient for input ", i);
+                Tensor &acc = grad_acc[inputs[i].impl.get()];
+                acc = acc.defined() ? binary(EW_ADD, acc.detach(), gis[i].detach()) : gis[i].detach();
+                if (--needed[inputs[i].impl.get()] == 0) ready.push(&inputs[i]);
+            }
+        } else if (t->requires_grad()) {
+            TensorImpl *impl = t->impl.get();
+            if (impl->grad) {
+                Tensor &gacc = *impl->grad;
+                run_binary(EW_ADD, gacc, gacc, go);
+            } else {
+                Tensor gcopy = empty(go.sizes(), go.dtype(), go.device());
+                run_copy(gcopy, go);
+                impl->grad.reset(new Tensor(gcopy));
+            }
+        }
+    }
+}
+
+}  // namespace ops
+}  // namespace kf

@@ -1,0 +1,66 @@
+// Operator front-ends (host): build a plan, call one kernel launcher, wire autograd.
+// Mirrors the reference's `gpu::` namespace (src/core/*_ops.cpp) function for function.
+#pragma once
+#include <tuple>
+
+#include "core.h"
+#include "kernels.h"
+
+namespace kf {
+namespace ops {
+
+// ---- planning (ref: TensorIterator::build, src/core/tensor_iterator.cpp:486-515)
+// Fills the collapsed plan for out = f(a, b).  `out` undefined => allocated (contiguous, promoted dtype).
+void plan_elementwise(EwPlan &plan, Tensor &out, const Tensor *a, const Tensor *b, bool allow_resize_check);
+
+// ---- elementwise
+Tensor binary(int op, const Tensor &a, const Tensor &b);
+Tensor &binary_(int op, Tensor &self, const Tensor &other);
+Tensor binary_scalar(int op, const Tensor &a, double scalar);
+Tensor &binary_scalar_(int op, Tensor &self, double scalar);
+Tensor &fill_(Tensor &self, double value);
+Tensor &copy_(Tensor &self, const Tensor &src);
+Tensor clone(const Tensor &self);
+Tensor convert(const Tensor &self, DType dtype);
+Tensor unary(int op, const Tensor &a);
+inline Tensor add(const Tensor &a, const Tensor &b) { return binary(EW_ADD, a, b); }
+inline Tensor sub(const Tensor &a, const Tensor &b) { return binary(EW_SUB, a, b); }
+inline Tensor mul(const Tensor &a, const Tensor &b) { return binary(EW_MUL, a, b); }
+inline Tensor div(const Tensor &a, const Tensor &b) { return binary(EW_DIV, a, b); }
+
+// ---- reductions (keepdim)
+Tensor sum(const Tensor &self, int64_t dim);
+Tensor mean(const Tensor &self, int64_t dim);
+std::tuple<Tensor, Tensor> mean_var(const Tensor &self, int64_t dim, bool take_sqrt);
+std::tuple<Tensor, Tensor> norm_stat(const Tensor &self, int64_t dim);
+// reduce `grad` (shape = broadcast result) back to `shape` by summing broadcast dims (autograd helper)
+Tensor sum_to_shape(const Tensor &grad, const std::vector<int64_t> &shape);
+
+// ---- sort / top-k
+std::tuple<Tensor, Tensor> sort(const Tensor &self, int64_t dim, bool descending);
+std::tuple<Tensor, Tensor> topk(const Tensor &self, int64_t k, int64_t dim, bool largest);
+
+// ---- shape ops
+Tensor cat(const std::vector<Tensor> &tensors, int64_t dim);
+std::vector<Tensor> split(const Tensor &self, const std::vector<int64_t> &sizes, int64_t dim);
+Tensor &index_put_(Tensor &self, const std::vector<Tensor> &indices, const Tensor &values);
+// differentiable view wrappers (the raw view algebra on Tensor carries no grad_fn)
+Tensor permute(const Tensor &self, const std::vector<int64_t> &dims);
+Tensor view(const Tensor &self, const std::vector<int64_t> &sizes);
+Tensor contiguous(const Tensor &self);
+Tensor slice(const Tensor &self, int64_t dim, int64_t start, int64_t end, int64_t step);
+
+// ---- contractions
+Tensor gemm(const Tensor &a, const Tensor &b, float alpha, float beta);
+void gemm_out(Tensor &out, const Tensor &a, const Tensor &b, float alpha, float beta);
+Tensor matmul(const Tensor &a, bool trans_a, const Tensor &b, bool trans_b, float alpha);
+Tensor causal_attention(const Tensor &q, const Tensor &k, const Tensor &v);
+std::tuple<Tensor, Tensor> causal_attention_fwd(const Tensor &q, const Tensor &k, const Tensor &v);
+std::tuple<Tensor, Tensor, Tensor> causal_attention_bwd(const Tensor &dout, const Tensor &q, const Tensor &k, const Tensor &v,
+                                                        const Tensor &out, const Tensor &lse);
+
+// ---- autograd (ref: Tensor::backward, src/core/tensor.cpp:86-126)
+void backward(Tensor &root, const Tensor &grad_output);
+
+}  // namespace ops
+}  // namespace kf

@@ -87,9 +87,10 @@ int kf_empty_like(kf_tensor_t self, kf_tensor_t *out);
 int kf_from_host(const void *src, const int64_t *shape, int ndim, int dtype, int device, kf_tensor_t *out);
 /* tensor (must be contiguous) -> host buffer of numel*itemsize bytes (ref: to_numpy, register.cpp:41-57) */
 int kf_to_host(kf_tensor_t self, void *dst, size_t dst_bytes);
-/* asynchronous variants on the library stream: host memory must be pinned; no implicit sync */
-int kf_copy_from_host_async(kf_tensor_t self, const void *src, size_t bytes);
-int kf_copy_to_host_async(kf_tensor_t self, void *dst, size_t bytes);
+/* raw asynchronous copies on the library stream, no implicit sync; host memory should be pinned
+ * (ref: dmemcpy_h2d / dmemcpy_d2h, src/device/memory_engine.cu:14-24, which create+destroy a stream per copy) */
+int kf_memcpy_h2d_async(void *dst_device, const void *src_host, size_t bytes);
+int kf_memcpy_d2h_async(void *dst_host, const void *src_device, size_t bytes);
 
 /* ---- handles / metadata (ref: tensor.h:42-124, register.cpp:88-139) ------------------------ */
 int kf_retain(kf_tensor_t self, kf_tensor_t *out); /* new handle, same impl (ref: Tensor copy ctor, register.cpp:89-90) */

@@ -194,18 +194,14 @@ int kf_to_host(kf_tensor_t self, void *dst, size_t dst_bytes) {
     Runtime::get().d2h(dst, t.data(), bytes, true);
     KF_API_END
 }
-int kf_copy_from_host_async(kf_tensor_t self, const void *src, size_t bytes) {
+int kf_memcpy_h2d_async(void *dst_device, const void *src_host, size_t bytes) {
     KF_API_BEGIN
-    Tensor &t = T(self);
-    KF_CHECK(t.is_contiguous() && bytes == (size_t)t.numel() * t.itemsize());
-    Runtime::get().h2d(t.data(), src, bytes, false);
+    Runtime::get().h2d(dst_device, src_host, bytes, false);
     KF_API_END
 }
-int kf_copy_to_host_async(kf_tensor_t self, void *dst, size_t bytes) {
+int kf_memcpy_d2h_async(void *dst_host, const void *src_device, size_t bytes) {
     KF_API_BEGIN
-    Tensor &t = T(self);
-    KF_CHECK(t.is_contiguous() && bytes == (size_t)t.numel() * t.itemsize());
-    Runtime::get().d2h(dst, t.data(), bytes, false);
+    Runtime::get().d2h(dst_host, src_device, bytes, false);
     KF_API_END
 }
 

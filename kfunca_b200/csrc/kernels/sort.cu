@@ -1,0 +1,592 @@
+// sm_100a stable sort and top-k along dense rows.
+// Replaces the reference's BlockRadixSort / upsweep-scan-downsweep family and topk_with_sort
+// (src/device/sort_ops_kernel.cu:12-632, src/device/utils/sorting_radix_sort.h:7-905).
+//
+// Ordering contract (bit-exact with the reference): keys are mapped to order-preserving unsigned integers
+// (KeyTraits, src/device/utils/sorting_common.h:39-238); the sort is stable; "descending" is a stable sort of
+// the complemented key, so ties always keep ascending original index; indices are int64.
+//
+//   rows <= 4096 elements : one CTA per row, bitonic network in shared memory on the composite (key, index)
+//                           — the index makes every element unique, so the network is deterministic & stable.
+//   longer rows           : LSD radix sort, 8-bit digits (half the passes of the reference's 4-bit digits):
+//                           per pass  tile histogram -> per-row exclusive scan -> stable scatter, where the
+//                           in-tile stable rank comes from warp match_any + per-warp running digit counts.
+//   top-k (k <= 1024, 2048 <= n <= 32768): ONE pass over HBM.  The whole row lives in registers (32 keys x 1024
+//                           threads); a lower bound T0 of the k-th key is derived from per-thread maxima
+//                           (warp w contributes its ceil(k/32)-th largest thread-max, T0 = min over warps, which
+//                           guarantees >= k elements >= T0); elements >= T0 (a few hundred) are compacted to shared
+//                           memory, rank-sorted by (key desc, index asc) and the first k written.  Rows whose
+//                           candidate set overflows (massive ties) are redone exactly by a radix-select kernel.
+#include <algorithm>
+
+#include "ew_common.cuh"
+
+namespace kf {
+
+enum KeyKind { KEY_UINT = 0, KEY_SINT = 1, KEY_FLOAT = 2 };
+
+template <typename U>
+__device__ __forceinline__ U key_convert(U x, int kind, bool descending) {
+    constexpr int B = sizeof(U) * 8;
+    const U sign = U(1) << (B - 1);
+    U k;
+    if (kind == KEY_FLOAT) k = (x & sign) ? U(~x) : U(x | sign);
+    else if (kind == KEY_SINT) k = x ^ sign;
+    else k = x;
+    return descending ? U(~k) : k;
+}
+template <typename U>
+__device__ __forceinline__ U key_deconvert(U k, int kind, bool descending) {
+    constexpr int B = sizeof(U) * 8;
+    const U sign = U(1) << (B - 1);
+    if (descending) k = U(~k);
+    if (kind == KEY_FLOAT) return (k & sign) ? U(k ^ sign) : U(~k);
+    if (kind == KEY_SINT) return k ^ sign;
+    return k;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small rows: bitonic sort of (key, idx) in shared memory
+// ------------------------------------------------------------------------------------------------
+template <typename U>
+__global__ void sort_rows_bitonic_kernel(const U *__restrict__ in, U *__restrict__ values, int64_t *__restrict__ indices,
+                                         const int n, const int N, const int kind, const bool descending) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    U *sk = reinterpret_cast<U *>(smem_raw);
+    uint32_t *si = reinterpret_cast<uint32_t *>(smem_raw + (size_t)N * sizeof(U));
+    const int64_t row = blockIdx.x;
+    const U *src = in + row * n;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        if (i < n) {
+            sk[i] = key_convert<U>(src[i], kind, descending);
+            si[i] = (uint32_t)i;
+        } else {
+            sk[i] = U(~U(0));
+            si[i] = 0x80000000u + (uint32_t)i;  // pads sort after every real element, even on equal keys
+        }
+    }
+    __syncthreads();
+    for (int k = 2; k <= N; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (N >> 1); t += blockDim.x) {
+                const int i = 2 * t - (t & (j - 1));
+                const int l = i + j;
+                const bool up = (i & k) == 0;
+                const U ki = sk[i], kl = sk[l];
+                const uint32_t ii = si[i], il = si[l];
+                const bool gt = ki > kl || (ki == kl && ii > il);
+                if (gt == up) {
+                    sk[i] = kl; sk[l] = ki;
+                    si[i] = il; si[l] = ii;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        values[row * n + i] = key_deconvert<U>(sk[i], kind, descending);
+        indices[row * n + i] = (int64_t)si[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// long rows: LSD radix sort, 8-bit digits
+// ------------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per CTA
+
+struct RadixArgs {
+    const void *keys_in;   // U keys (pass 0: raw input bits)
+    const uint32_t *idx_in;
+    void *keys_out;        // U keys, or raw value bits on the last pass
+    uint32_t *idx_out;
+    int64_t *idx_out64;    // last pass
+    uint32_t *hist;        // [nseg][256][tiles]
+    int n, tiles, shift, kind;
+    bool descending, first, last;
+};
+
+template <typename U>
+__device__ __forceinline__ U radix_load_key(const RadixArgs &a, int64_t base, int i) {
+    const U raw = reinterpret_cast<const U *>(a.keys_in)[base + i];
+    return a.first ? key_convert<U>(raw, a.kind, a.descending) : raw;
+}
+
+template <typename U>
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const RadixArgs a) {
+    __shared__ uint32_t hist[256];
+    const int tile = blockIdx.x;
+    const int64_t seg = blockIdx.y;
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = seg * a.n;
+    const int lo = tile * RS_TILE;
+    const int lane = threadIdx.x & 31;
+#pragma unroll 4
+    for (int it = 0; it < RS_ITEMS; ++it) {
+        const int i = lo + it * RS_THREADS + threadIdx.x;
+        uint32_t d = 256;
+        if (i < a.n) d = (uint32_t)((radix_load_key<U>(a, base, i) >> a.shift) & 0xff);
+        const uint32_t m = __match_any_sync(0xffffffffu, d);
+        if (d < 256 && lane == __ffs(m) - 1) atomicAdd(&hist[d], __popc(m));
+    }
+    __syncthreads();
+    a.hist[(seg * 256 + threadIdx.x) * a.tiles + tile] = hist[threadIdx.x];
+}
+
+// exclusive scan of hist[seg][digit][tile] in (digit, tile) order, in place; one CTA per row
+__global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t *__restrict__ hist, const int len) {
+    __shared__ uint32_t warp_tot[32];
+    uint32_t *h = hist + (int64_t)blockIdx.x * len;
+    const int chunk = (len + 1023) / 1024;
+    const int lo = threadIdx.x * chunk;
+    const int hi = min(lo + chunk, len);
+    uint32_t s = 0;
+    for (int i = lo; i < hi; ++i) s += h[i];
+    // block exclusive scan of s
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t v = warp_tot[lane], vi = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, vi, o);
+            if (lane >= o) vi += u;
+        }
+        warp_tot[lane] = vi - v;
+    }
+    __syncthreads();
+    uint32_t run = warp_tot[w] + inc - s;
+    for (int i = lo; i < hi; ++i) {
+        const uint32_t c = h[i];
+        h[i] = run;
+        run += c;
+    }
+}
+
+template <typename U>
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const RadixArgs a) {
+    __shared__ uint32_t wcnt[RS_WARPS][257];
+    __shared__ uint32_t gbase[256];
+    const int tile = blockIdx.x;
+    const int64_t seg = blockIdx.y;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < RS_WARPS * 257; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
+    gbase[threadIdx.x] = a.hist[(seg * 256 + threadIdx.x) * a.tiles + tile];
+    __syncthreads();
+    const int64_t base = seg * a.n;
+    // warp w owns the contiguous chunk [lo, lo + 32*RS_ITEMS); order inside the tile is (warp, item, lane)
+    const int lo = tile * RS_TILE + w * (32 * RS_ITEMS);
+    U key[RS_ITEMS];
+    uint32_t idx[RS_ITEMS];
+    uint32_t loc[RS_ITEMS];  // rank among same-digit keys of this warp
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; ++it) {
+        const int i = lo + it * 32 + lane;
+        uint32_t d = 256;
+        key[it] = 0;
+        idx[it] = 0;
+        if (i < a.n) {
+            key[it] = radix_load_key<U>(a, base, i);
+            idx[it] = a.first ? (uint32_t)i : a.idx_in[base + i];
+            d = (uint32_t)((key[it] >> a.shift) & 0xff);
+        }
+        const uint32_t m = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(m) - 1;
+        uint32_t old = 0;
+        if (lane == leader) {
+            old = wcnt[w][d];
+            wcnt[w][d] = old + __popc(m);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        loc[it] = old + __popc(m & ((1u << lane) - 1));
+        __syncwarp();
+    }
+    __syncthreads();
+    // exclusive prefix over warps, per digit (thread t owns digit t), folded with the global tile base
+    {
+        uint32_t run = gbase[threadIdx.x];
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ++ww) {
+            const uint32_t c = wcnt[ww][threadIdx.x];
+            wcnt[ww][threadIdx.x] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; ++it) {
+        const int i = lo + it * 32 + lane;
+        if (i < a.n) {
+            const uint32_t d = (uint32_t)((key[it] >> a.shift) & 0xff);
+            const int64_t pos = base + wcnt[w][d] + loc[it];
+            if (a.last) {
+                reinterpret_cast<U *>(a.keys_out)[pos] = key_deconvert<U>(key[it], a.kind, a.descending);
+                a.idx_out64[pos] = (int64_t)idx[it];
+            } else {
+                reinterpret_cast<U *>(a.keys_out)[pos] = key[it];
+                a.idx_out[pos] = idx[it];
+            }
+        }
+    }
+}
+
+template <typename U>
+static void sort_rows_typed(const void *in, void *values, int64_t *indices, int kind, int64_t nseg, int64_t n, bool descending) {
+    Runtime &rt = Runtime::get();
+    cudaStream_t st = rt.stream();
+    if (n <= 4096) {
+        int N = 32;
+        while (N < n) N <<= 1;
+        const int threads = std::max(32, std::min(N / 2, 1024));
+        const size_t smem = (size_t)N * (sizeof(U) + 4);
+        static bool attr_set = false;
+        if (!attr_set) {
+            KF_CUDA(cudaFuncSetAttribute(sort_rows_bitonic_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 12));
+            attr_set = true;
+        }
+        KF_CHECK(nseg < (int64_t)0x7FFFFFFF);
+        sort_rows_bitonic_kernel<U><<<(unsigned)nseg, threads, smem, st>>>((const U *)in, (U *)values, indices, (int)n, N, kind, descending);
+        rt.post_launch("sort_rows_bitonic_kernel");
+        return;
+    }
+    const int tiles = (int)((n + RS_TILE - 1) / RS_TILE);
+    const int64_t total = nseg * n;
+    Scratch kbuf0(total * sizeof(U)), kbuf1(total * sizeof(U)), ibuf0(total * 4), ibuf1(total * 4);
+    const int passes = (int)sizeof(U);
+    for (int64_t s0 = 0; s0 < nseg; s0 += 32768) {  // grid.y limit
+        const int64_t ns = std::min<int64_t>(32768, nseg - s0);
+        Scratch hist((size_t)ns * 256 * tiles * 4);
+        void *kb[2] = {(char *)kbuf0.p + s0 * n * sizeof(U), (char *)kbuf1.p + s0 * n * sizeof(U)};
+        uint32_t *ib[2] = {ibuf0.as<uint32_t>() + s0 * n, ibuf1.as<uint32_t>() + s0 * n};
+        for (int p = 0; p < passes; ++p) {
+            RadixArgs a{};
+            a.first = p == 0;
+            a.last = p == passes - 1;
+            a.keys_in = a.first ? (const void *)((const char *)in + s0 * n * sizeof(U)) : kb[(p + 1) & 1];
+            a.idx_in = ib[(p + 1) & 1];
+            a.keys_out = a.last ? (void *)((char *)values + s0 * n * sizeof(U)) : kb[p & 1];
+            a.idx_out = ib[p & 1];
+            a.idx_out64 = indices + s0 * n;
+            a.hist = hist.as<uint32_t>();
+            a.n = (int)n;
+            a.tiles = tiles;
+            a.shift = 8 * p;
+            a.kind = kind;
+            a.descending = descending;
+            dim3 grid((unsigned)tiles, (unsigned)ns);
+            radix_hist_kernel<U><<<grid, RS_THREADS, 0, st>>>(a);
+            rt.post_launch("radix_hist_kernel");
+            radix_scan_kernel<<<(unsigned)ns, 1024, 0, st>>>(hist.as<uint32_t>(), 256 * tiles);
+            rt.post_launch("radix_scan_kernel");
+            radix_scatter_kernel<U><<<grid, RS_THREADS, 0, st>>>(a);
+            rt.post_launch("radix_scatter_kernel");
+        }
+    }
+}
+
+static void key_class(int dtype, int &bytes, int &kind) {
+    switch (dtype) {
+    case KF_BYTE: bytes = 1; kind = KEY_UINT; break;
+    case KF_CHAR: bytes = 1; kind = KEY_SINT; break;
+    case KF_SHORT: bytes = 2; kind = KEY_SINT; break;
+    case KF_INT: bytes = 4; kind = KEY_SINT; break;
+    case KF_LONG: bytes = 8; kind = KEY_SINT; break;
+    case KF_HALF: case KF_BFLOAT16: bytes = 2; kind = KEY_FLOAT; break;
+    case KF_FLOAT: bytes = 4; kind = KEY_FLOAT; break;
+    case KF_DOUBLE: bytes = 8; kind = KEY_FLOAT; break;
+    default: KF_CHECK(false, "Sort currently does not support ", dtype_name(dtype), " dtypes.");
+    }
+}
+
+void launch_sort_rows(const void *in, void *values, int64_t *indices, int dtype, int64_t nseg, int64_t n, bool descending) {
+    if (nseg == 0 || n == 0) return;
+    int bytes, kind;
+    key_class(dtype, bytes, kind);
+    switch (bytes) {
+    case 1: sort_rows_typed<uint8_t>(in, values, indices, kind, nseg, n, descending); break;
+    case 2: sort_rows_typed<uint16_t>(in, values, indices, kind, nseg, n, descending); break;
+    case 4: sort_rows_typed<uint32_t>(in, values, indices, kind, nseg, n, descending); break;
+    default: sort_rows_typed<uint64_t>(in, values, indices, kind, nseg, n, descending); break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// top-k: register-resident single-pass select
+// ------------------------------------------------------------------------------------------------
+constexpr int TK_THREADS = 1024;
+constexpr int TK_CAP = 2048;  // candidate capacity in shared memory
+
+template <typename U>
+__device__ __forceinline__ bool cand_greater(U ka, uint32_t ia, U kb, uint32_t ib) {  // (key desc, index asc) order
+    return ka > kb || (ka == kb && ia < ib);
+}
+
+// sort the c candidates in (ck, ci) and write the first k; all threads of the CTA participate
+template <typename U>
+__device__ void emit_topk(U *ck, uint32_t *ci, const int c, const int k, U *__restrict__ out_v, int64_t *__restrict__ out_i,
+                          const int kind, const bool desc_key) {
+    if (c <= TK_THREADS) {
+        // rank sort: candidate t counts how many candidates precede it; broadcast shared-memory reads
+        if ((int)threadIdx.x < c) {
+            const U mk = ck[threadIdx.x];
+            const uint32_t mi = ci[threadIdx.x];
+            int rank = 0;
+            for (int j = 0; j < c; ++j) rank += cand_greater<U>(ck[j], ci[j], mk, mi) ? 1 : 0;
+            if (rank < k) {
+                out_v[rank] = key_deconvert<U>(mk, kind, desc_key);
+                out_i[rank] = (int64_t)mi;
+            }
+        }
+        return;
+    }
+    int N = 2048;  // c in (1024, 2048]
+    for (int i = c + threadIdx.x; i < N; i += blockDim.x) {
+        ck[i] = 0;
+        ci[i] = 0xffffffffu;  // pads are the smallest possible candidates
+    }
+    __syncthreads();
+    for (int kk = 2; kk <= N; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (N >> 1); t += blockDim.x) {
+                const int i = 2 * t - (t & (j - 1));
+                const int l = i + j;
+                const bool up = (i & kk) == 0;  // "up" = candidate order (best first)
+                const U ki = ck[i], kl = ck[l];
+                const uint32_t ii = ci[i], il = ci[l];
+                const bool l_first = cand_greater<U>(kl, il, ki, ii);
+                if (l_first == up) {
+                    ck[i] = kl; ck[l] = ki;
+                    ci[i] = il; ci[l] = ii;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        out_v[i] = key_deconvert<U>(ck[i], kind, desc_key);
+        out_i[i] = (int64_t)ci[i];
+    }
+}
+
+template <typename U, int ITEMS, bool VEC4>
+__global__ void __launch_bounds__(TK_THREADS, 1)
+topk_select_kernel(const U *__restrict__ in, U *__restrict__ values, int64_t *__restrict__ indices, const int n, const int k,
+                   const int kind, const bool largest, int *__restrict__ overflow_rows) {
+    __shared__ U ck[TK_CAP];
+    __shared__ uint32_t ci[TK_CAP];
+    __shared__ U warp_thr[32];
+    __shared__ int count;
+    const int64_t row = blockIdx.x;
+    const U *src = in + row * n;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    // descending order on keys == "largest"; for smallest we complement so that the same code selects maxima
+    const bool desc_key = !largest;  // key_convert(.., descending=true) complements
+    U key[ITEMS];
+    if (tid == 0) count = 0;
+    if constexpr (VEC4) {
+#pragma unroll
+        for (int i = 0; i < ITEMS / 4; ++i) {
+            const int p = (i * TK_THREADS + tid) * 4;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            const bool ok = p < n;  // n % 4 == 0 on this path
+            if (ok) v = *reinterpret_cast<const uint4 *>(src + p);
+            key[4 * i + 0] = ok ? key_convert<U>((U)v.x, kind, desc_key) : U(0);
+            key[4 * i + 1] = ok ? key_convert<U>((U)v.y, kind, desc_key) : U(0);
+            key[4 * i + 2] = ok ? key_convert<U>((U)v.z, kind, desc_key) : U(0);
+            key[4 * i + 3] = ok ? key_convert<U>((U)v.w, kind, desc_key) : U(0);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const int p = i * TK_THREADS + tid;
+            key[i] = p < n ? key_convert<U>(src[p], kind, desc_key) : U(0);
+        }
+    }
+    U tmax = 0;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) tmax = key[i] > tmax ? key[i] : tmax;
+    // j-th largest thread-max of this warp, j = ceil(k / 32): strict total order by (value, lane)
+    const int j = (k + 31) >> 5;
+    int rank = 0;
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+        const U v = __shfl_sync(0xffffffffu, tmax, l);
+        rank += (v > tmax || (v == tmax && l < lane)) ? 1 : 0;
+    }
+    if (rank == j - 1) warp_thr[w] = tmax;
+    __syncthreads();
+    U t0 = warp_thr[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const U v = __shfl_xor_sync(0xffffffffu, t0, o);
+        t0 = v < t0 ? v : t0;
+    }
+    // compact everything >= t0 (at least k elements by construction)
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        if (key[i] >= t0) {
+            const int p = VEC4 ? ((i / 4) * TK_THREADS + tid) * 4 + (i & 3) : i * TK_THREADS + tid;
+            if (p < n) {
+                const int slot = atomicAdd(&count, 1);
+                if (slot < TK_CAP) {
+                    ck[slot] = key[i];
+                    ci[slot] = (uint32_t)p;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int c = count;
+    if (c > TK_CAP) {  // massive ties: hand the row to the exact kernel
+        if (tid == 0) overflow_rows[row] = 1;
+        return;
+    }
+    emit_topk<U>(ck, ci, c, k, values + row * k, indices + row * k, kind, desc_key);
+}
+
+// exact radix-select top-k straight from global memory (any n, k <= TK_CAP); used for overflowed rows
+template <typename U>
+__global__ void __launch_bounds__(TK_THREADS, 1)
+topk_exact_kernel(const U *__restrict__ in, U *__restrict__ values, int64_t *__restrict__ indices, const int n, const int k,
+                  const int kind, const bool largest, const int *__restrict__ only_rows) {
+    __shared__ U ck[TK_CAP];
+    __shared__ uint32_t ci[TK_CAP];
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t scan_w[32];
+    __shared__ U s_prefix;
+    __shared__ int s_need, s_count, s_eq_taken;
+    const int64_t row = blockIdx.x;
+    if (only_rows && !only_rows[row]) return;
+    const U *src = in + row * n;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const bool desc_key = !largest;
+    constexpr int B = sizeof(U) * 8;
+    U prefix = 0;     // decided high bits of the k-th largest key
+    int need = k;     // rank (1-based) of the wanted key among keys matching the decided prefix
+    for (int shift = B - 8; shift >= 0; shift -= 8) {
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+        const U hi_mask = (shift + 8 >= B) ? U(0) : U(~U(0)) << (shift + 8);
+        for (int i = tid; i < n; i += TK_THREADS) {
+            const U kx = key_convert<U>(src[i], kind, desc_key);
+            if ((kx & hi_mask) == (prefix & hi_mask)) atomicAdd(&hist[(uint32_t)((kx >> shift) & 0xff)], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int acc = 0, d = 255;
+            for (; d > 0; --d) {
+                if (acc + (int)hist[d] >= need) break;
+                acc += (int)hist[d];
+            }
+            s_prefix = prefix | (U(d) << shift);
+            s_need = need - acc;
+        }
+        __syncthreads();
+        prefix = s_prefix;
+        need = s_need;
+        __syncthreads();
+    }
+    // prefix == k-th largest key; `need` of the elements equal to it are wanted, lowest indices first
+    if (tid == 0) {
+        s_count = 0;
+        s_eq_taken = 0;
+    }
+    __syncthreads();
+    for (int base = 0; base < n; base += TK_THREADS) {
+        const int i = base + tid;
+        U kx = 0;
+        bool gt = false, eq = false;
+        if (i < n) {
+            kx = key_convert<U>(src[i], kind, desc_key);
+            gt = kx > prefix;
+            eq = kx == prefix;
+        }
+        if (gt) {
+            const int slot = atomicAdd(&s_count, 1);
+            ck[slot] = kx;
+            ci[slot] = (uint32_t)i;
+        }
+        // ordered ranking of the equal keys inside this chunk
+        const uint32_t bal = __ballot_sync(0xffffffffu, eq);
+        if (lane == 0) scan_w[w] = __popc(bal);
+        __syncthreads();
+        int before = s_eq_taken;
+        for (int ww = 0; ww < w; ++ww) before += (int)scan_w[ww];
+        const int my = before + __popc(bal & ((1u << lane) - 1));
+        if (eq && my < need) {
+            const int slot = atomicAdd(&s_count, 1);
+            ck[slot] = kx;
+            ci[slot] = (uint32_t)i;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int ww = 0; ww < 32; ++ww) tot += (int)scan_w[ww];
+            s_eq_taken += tot;
+        }
+        __syncthreads();
+    }
+    emit_topk<U>(ck, ci, s_count, k, values + row * k, indices + row * k, kind, desc_key);
+}
+
+template <typename U>
+static bool topk_typed(const void *in, void *values, int64_t *indices, int kind, int64_t nseg, int64_t n, int64_t k, bool largest) {
+    Runtime &rt = Runtime::get();
+    cudaStream_t st = rt.stream();
+    KF_CHECK(nseg < (int64_t)0x7FFFFFFF);
+    const unsigned grid = (unsigned)nseg;
+    const bool fast = k <= 1024 && n >= 2048 && n <= 32 * TK_THREADS;
+    if (!fast) {
+        // rows too long for registers: exact select when k fits the candidate buffer and rows are long enough to pay
+        if (k <= 1024 && n > 32 * TK_THREADS) {
+            topk_exact_kernel<U><<<grid, TK_THREADS, 0, st>>>((const U *)in, (U *)values, indices, (int)n, (int)k, kind, largest, nullptr);
+            rt.post_launch("topk_exact_kernel");
+            return true;
+        }
+        return false;
+    }
+    Scratch flags((size_t)nseg * sizeof(int));
+    rt.memset_async(flags.p, 0, (size_t)nseg * sizeof(int));
+    const bool vec = sizeof(U) == 4 && n % 4 == 0 && ((uintptr_t)in % 16 == 0);
+    int items = 4;
+    while ((int64_t)items * TK_THREADS < n) items *= 2;
+#define KF_TOPK_LAUNCH(IT)                                                                                                    \
+    do {                                                                                                                      \
+        if (vec) topk_select_kernel<U, IT, true><<<grid, TK_THREADS, 0, st>>>((const U *)in, (U *)values, indices, (int)n, (int)k, kind, largest, flags.as<int>()); \
+        else topk_select_kernel<U, IT, false><<<grid, TK_THREADS, 0, st>>>((const U *)in, (U *)values, indices, (int)n, (int)k, kind, largest, flags.as<int>()); \
+    } while (0)
+    switch (items) {
+    case 4: KF_TOPK_LAUNCH(4); break;
+    case 8: KF_TOPK_LAUNCH(8); break;
+    case 16: KF_TOPK_LAUNCH(16); break;
+    default: KF_TOPK_LAUNCH(32); break;
+    }
+#undef KF_TOPK_LAUNCH
+    rt.post_launch("topk_select_kernel");
+    topk_exact_kernel<U><<<grid, TK_THREADS, 0, st>>>((const U *)in, (U *)values, indices, (int)n, (int)k, kind, largest, flags.as<int>());
+    rt.post_launch("topk_exact_kernel");
+    return true;
+}
+
+bool launch_topk_rows(const void *in, void *values, int64_t *indices, int dtype, int64_t nseg, int64_t n, int64_t k, bool largest) {
+    int bytes, kind;
+    key_class(dtype, bytes, kind);
+    switch (bytes) {
+    case 1: return topk_typed<uint8_t>(in, values, indices, kind, nseg, n, k, largest);
+    case 2: return topk_typed<uint16_t>(in, values, indices, kind, nseg, n, k, largest);
+    case 4: return topk_typed<uint32_t>(in, values, indices, kind, nseg, n, k, largest);
+    default: return topk_typed<uint64_t>(in, values, indices, kind, nseg, n, k, largest);
+    }
+}
+
+}  // namespace kf

@@ -1,9 +1,6 @@
 // temporary stubs, replaced as the real kernels land
 #include "ew_common.cuh"
 namespace kf {
-void launch_sort_rows(const void *, void *, int64_t *, int, int64_t, int64_t, bool) { KF_CHECK(false, "sort kernel not built yet"); }
-bool launch_topk_rows(const void *, void *, int64_t *, int, int64_t, int64_t, int64_t, bool) { return false; }
-void launch_gemm(const GemmPlan &) { KF_CHECK(false, "gemm kernel not built yet"); }
 void launch_attention_fwd(const AttnPlan &) { KF_CHECK(false, "attention kernel not built yet"); }
 void launch_attention_bwd(const AttnBwdPlan &) { KF_CHECK(false, "attention bwd kernel not built yet"); }
 }

@@ -89,20 +89,22 @@ void launch_gemm(const GemmPlan &p);       // dispatcher
 struct AttnPlan {
     const void *q, *k, *v;
     void *out;
-    float *lse;  // [BH, Sq] natural-log LSE, may be null
+    void *lse;  // [BH, Sq] natural-log row log-sum-exp, fp32 (fp64 for fp64 inputs); may be null
     int dtype;
     int64_t BH, Sq, Skv, D;
 };
-void launch_attention_fwd(const AttnPlan &p);
-bool launch_attention_fwd_tc(const AttnPlan &p);
+void launch_attention_fwd(const AttnPlan &p);     // dispatcher: tcgen05 path for 16-bit D in {64,128}, else SIMT
+bool launch_attention_fwd_tc(const AttnPlan &p);  // false when the shape / dtype is not supported
 struct AttnBwdPlan {
     const void *q, *k, *v, *out, *dout;
-    const float *lse;
+    const void *lse;
     void *dq, *dk, *dv;
     int dtype;
     int64_t BH, Sq, Skv, D;
 };
-void launch_attention_bwd(const AttnBwdPlan &p);
+bool launch_attention_bwd_tc(const AttnBwdPlan &p);  // false => caller uses the GEMM-composed generic backward
+// P = exp(S - lse) under the causal mask, in place, fp32 / fp64 (generic backward helper)
+void launch_attn_probs(void *S, const void *lse, int dtype, int64_t BH, int64_t Sq, int64_t Skv);
 
 std::string device_info_string();
 

@@ -734,10 +734,10 @@ std::tuple<Tensor, Tensor> causal_attention_fwd(const Tensor &q_, const Tensor &
     check_attention(q_, k_, v_);
     Tensor q = q_.detach().contiguous(), k = k_.detach().contiguous(), v = v_.detach().contiguous();
     Tensor out = empty(q.sizes(), q.dtype(), q.device());
-    Tensor lse = empty({q.size(0), q.size(1), q.size(2)}, KF_FLOAT, q.device());
+    Tensor lse = empty({q.size(0), q.size(1), q.size(2)}, q.dtype() == KF_DOUBLE ? KF_DOUBLE : KF_FLOAT, q.device());
     AttnPlan p{};
     p.q = q.data(); p.k = k.data(); p.v = v.data(); p.out = out.data();
-    p.lse = lse.data_as<float>();
+    p.lse = lse.data();
     p.dtype = q.dtype();
     p.BH = q.size(0) * q.size(1);
     p.Sq = q.size(2);
@@ -761,26 +761,54 @@ Tensor causal_attention(const Tensor &q, const Tensor &k, const Tensor &v) {
     return out;
 }
 
+// Generic backward: the five GEMMs of attention backward issued through our own GEMM kernels on fp32 (fp64)
+// temporaries, one batch entry at a time so the S_q x S_kv scratch stays bounded.  Any shape / dtype.
+// (The reference has no attention backward at all)
+static void attention_bwd_generic(const Tensor &dout, const Tensor &q, const Tensor &k, const Tensor &v, const Tensor &o,
+                                  const Tensor &lse, Tensor &dq, Tensor &dk, Tensor &dv) {
+    const DType ct = q.dtype() == KF_DOUBLE ? KF_DOUBLE : KF_FLOAT;
+    const double scale = 1.0 / std::sqrt((double)q.size(3));
+    const int64_t B = q.size(0), H = q.size(1), Sq = q.size(2), Skv = k.size(2);
+    for (int64_t b = 0; b < B; ++b) {
+        auto cvt = [&](const Tensor &t) { return convert(t.narrow(0, b, 1), ct); };
+        Tensor qf = cvt(q), kf = cvt(k), vf = cvt(v), of = cvt(o), dof = cvt(dout);
+        Tensor lb = convert(lse.narrow(0, b, 1), ct).contiguous();
+        Tensor P = matmul(qf, false, kf, true, (float)scale);              // S = scale * Q K^T   [1,H,Sq,Skv]
+        launch_attn_probs(P.data(), lb.data(), ct, H, Sq, Skv);            // P = exp(S - lse), causal
+        Tensor dP = matmul(dof, false, vf, true, 1.f);                     // dP = dO V^T
+        Tensor delta = sum(binary(EW_MUL, dof, of), 3);                    // [1,H,Sq,1]
+        Tensor dS = binary_scalar(EW_MUL, binary(EW_MUL, P, binary(EW_SUB, dP, delta)), scale);
+        Tensor dvb = matmul(P, true, dof, false, 1.f);                     // dV = P^T dO
+        Tensor dkb = matmul(dS, true, qf, false, 1.f);                     // dK = dS^T Q
+        Tensor dqb = matmul(dS, false, kf, false, 1.f);                    // dQ = dS K
+        Tensor dq_dst = dq.narrow(0, b, 1), dk_dst = dk.narrow(0, b, 1), dv_dst = dv.narrow(0, b, 1);
+        run_copy(dq_dst, dqb);
+        run_copy(dk_dst, dkb);
+        run_copy(dv_dst, dvb);
+    }
+}
+
 std::tuple<Tensor, Tensor, Tensor> causal_attention_bwd(const Tensor &dout_, const Tensor &q_, const Tensor &k_, const Tensor &v_,
                                                         const Tensor &out_, const Tensor &lse_) {
     check_attention(q_, k_, v_);
     Tensor q = q_.detach().contiguous(), k = k_.detach().contiguous(), v = v_.detach().contiguous();
     Tensor o = out_.detach().contiguous(), dout = dout_.detach().contiguous(), lse = lse_.detach().contiguous();
     KF_CHECK(dout.sizes() == q.sizes() && o.sizes() == q.sizes() && dout.dtype() == q.dtype());
-    KF_CHECK(lse.dtype() == KF_FLOAT && lse.numel() == q.size(0) * q.size(1) * q.size(2));
+    KF_CHECK((lse.dtype() == KF_FLOAT || lse.dtype() == KF_DOUBLE) && lse.numel() == q.size(0) * q.size(1) * q.size(2));
     Tensor dq = empty(q.sizes(), q.dtype(), q.device());
     Tensor dk = empty(k.sizes(), k.dtype(), k.device());
     Tensor dv = empty(v.sizes(), v.dtype(), v.device());
+    if (q.numel() == 0 || k.numel() == 0) return {dq, dk, dv};
     AttnBwdPlan p{};
     p.q = q.data(); p.k = k.data(); p.v = v.data(); p.out = o.data(); p.dout = dout.data();
-    p.lse = lse.data_as<float>();
+    p.lse = lse.data();
     p.dq = dq.data(); p.dk = dk.data(); p.dv = dv.data();
     p.dtype = q.dtype();
     p.BH = q.size(0) * q.size(1);
     p.Sq = q.size(2);
     p.Skv = k.size(2);
     p.D = q.size(3);
-    if (q.numel() > 0) launch_attention_bwd(p);
+    if (!(lse.dtype() == KF_FLOAT && launch_attention_bwd_tc(p))) attention_bwd_generic(dout, q, k, v, o, lse, dq, dk, dv);
     return {dq, dk, dv};
 }
 

@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py — the driver's measurement contract for kfunca_b200.
+
+  python bench.py --gpus N --steps K --warmup W [--workload gemm|attention|elementwise|topk|block] [--impl reference]
+
+Headline workload (default, BASELINE.json configs[1]): bf16 matmul M=N=K=8192 through kfunca's operator API
+(`gemm(a, b[K,N], 1, 0)`), one GEMM per step, synthetic seeded data.
+  value     : TFLOP/s with A, B resident in HBM (CUDA events on the library stream, max over ranks)
+  e2e       : same metric through the public API with HOST buffers: per step H2D of A and B from pinned memory,
+              the GEMM, and D2H of C, all inside the timed region
+  roofline  : tensor-pipe roofline of the dominant kernel (gemm_tc_kernel) against MEASURED_PEAKS.json
+  cpu_baseline : NumPy (OpenBLAS, all host cores) fp32 matmul on a bounded M-slab of the same problem
+  extras    : the other BASELINE configs measured the same way (HBM GB/s for elementwise / sum / permute / top-k,
+              TFLOP/s for causal attention), each with its own roofline fraction
+N > 1 (torchrun): every rank multiplies its own M-slab (global M = 8192 * N, no data-path collective) -> weak scaling.
+`--impl reference` runs the UNMODIFIED reference build (oracle/_ref, built from /root/reference by oracle/Makefile) through its
+own Python API on the same GPU — fp32, because the reference has no 16-bit GEMM — and falls back to the NumPy
+oracle port when that build is not loadable.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_GEMM = 8192
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        busy = [x for x in sm if x > 0.5 * (max(mx) if mx else 1)] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def dist_setup(n):
+    if n <= 1:
+        return 0, 1, None
+    import torch
+    import torch.distributed as dist
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, dist
+
+
+def max_over_ranks(ms, dist):
+    if dist is None:
+        return ms
+    import torch
+
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(dist):
+    if dist is not None:
+        import torch
+
+        dist.barrier()
+        torch.cuda.synchronize()
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    rank, world, dist = dist_setup(args.gpus)
+    import kfunca_b200 as kf
+    from kfunca_b200.runtime import Event, PinnedBuffer, copy_from_host_async, copy_to_host_async, launch_count
+    from oracle import oracle as O  # bf16 host dtype + cpu_baseline leg only
+
+    peaks = measured_peaks()
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    kf.set_device(local)
+    rng = np.random.default_rng(1234 + rank)
+    n = N_GEMM
+    # synthetic inputs: U(-1,1) -> fp32 -> bf16; A and B together are 256 MiB > the 126 MB L2
+    a_host = PinnedBuffer((n, n), np.uint16)
+    b_host = PinnedBuffer((n, n), np.uint16)
+    c_host = PinnedBuffer((n, n), np.uint16)
+    a_host.array[:] = rng.uniform(-1, 1, (n, n)).astype(np.float32).astype(O.bfloat16).view(np.uint16)
+    b_host.array[:] = rng.uniform(-1, 1, (n, n)).astype(np.float32).astype(O.bfloat16).view(np.uint16)
+    A = kf.empty([n, n], kf.bfloat16, local)
+    B = kf.empty([n, n], kf.bfloat16, local)
+    copy_from_host_async(A, a_host)
+    copy_from_host_async(B, b_host)
+    kf.synchronize()
+    flops = 2.0 * n * n * n
+
+    def step():
+        return kf.gemm(A, B, 1.0, 0.0)
+
+    def step_e2e():
+        copy_from_host_async(A, a_host)
+        copy_from_host_async(B, b_host)
+        C = kf.gemm(A, B, 1.0, 0.0)
+        copy_to_host_async(c_host, C)
+        kf.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    kf.synchronize()
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    barrier(dist)
+    kf.synchronize()
+    l0 = launch_count()
+    e0, e1 = Event(), Event()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    e1.synchronize()
+    barrier(dist)
+    launches = launch_count() - l0
+    ms_total = max_over_ranks(e0.elapsed_ms(e1), dist)
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = world * flops / (ms_step * 1e-3) / 1e12
+
+    # end-to-end through the public API with host buffers
+    e2e_steps = max(3, min(args.steps, 10))
+    step_e2e()
+    barrier(dist)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(e2e_steps):
+        step_e2e()
+    e1.record()
+    e1.synchronize()
+    barrier(dist)
+    e2e_ms = max_over_ranks(e0.elapsed_ms(e1), dist) / e2e_steps
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    e2e_val = world * flops / (max(e2e_ms, e2e_wall_ms) * 1e-3) / 1e12
+
+    if rank != 0:
+        return
+    # parity spot-check of the timed configuration against the oracle (a few rows, float64)
+    C = step().float().numpy()
+    rows = [0, 4095, 8191]
+    af = a_host.array.view(O.bfloat16)[rows].astype(np.float64)
+    bf = b_host.array.view(O.bfloat16).astype(np.float64)
+    exact = af @ bf
+    parity_ok = bool(np.all(np.abs(C[rows] - exact) <= 2e-2 * np.abs(exact) + 2e-3 * (np.abs(af) @ np.abs(bf))))
+
+    peak = peaks["bf16_tflops"]
+    achieved = flops / (ms_step * 1e-3) / 1e12
+    out = {
+        "metric": "bf16 matmul TFLOPS (kfunca gemm, M=N=K=8192)", "value": round(value, 2), "unit": "TFLOP/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "bf16 matmul M=N=K=8192 per GPU (BASELINE.json configs[1]); A,B,C row-major, B is [K,N]",
+                   "l2": "A+B = 256 MiB > 126 MB L2, no flush needed", "seed": 1234, "parity_spot_check": parity_ok,
+                   "parallelism": f"dp{world} (independent M-slabs, no collective)"},
+        "e2e": {"value": round(e2e_val, 2), "unit": "TFLOP/s", "h2d_bytes_per_step": 2 * n * n * 2, "d2h_bytes_per_step": n * n * 2,
+                "ms_per_step": round(max(e2e_ms, e2e_wall_ms), 3)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
+                     "traffic": load_traffic("gemm_tc_kernel"), "peak_kind": "burst bf16 cuBLAS, " + peaks["source"],
+                     "kernel": "gemm_tc_kernel<256,false,true>"},
+    }
+    out["cpu_baseline"] = cpu_baseline_gemm(a_host.array.view(O.bfloat16), b_host.array.view(O.bfloat16))
+    if not args.no_extras and world == 1:
+        out["extras"] = extras(kf, Event, peaks)
+    print(json.dumps(out))
+
+
+def load_traffic(kernel):
+    """dram bytes per launch from the committed ncu capture (profiles/traffic.json), or null"""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        return json.load(open(path)).get(kernel)
+    return None
+
+
+def cpu_baseline_gemm(a_bf16, b_bf16, slab=1024):
+    """NumPy fp32 matmul (OpenBLAS on all host cores) on an M-slab of the same operands: 2*slab*8192^2 FLOP."""
+    a = a_bf16[:slab].astype(np.float32)
+    b = b_bf16.astype(np.float32)
+    a @ b[:, :256]  # warm the BLAS threads
+    best = 1e30
+    for _ in range(2):
+        t0 = time.perf_counter()
+        a @ b
+        best = min(best, time.perf_counter() - t0)
+    return {"value": round(2.0 * slab * N_GEMM * N_GEMM / best / 1e12, 4), "unit": "TFLOP/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"np.matmul fp32, M-slab {slab} x K 8192 x N 8192 of the same operands (best of 2, {best:.2f} s)"}
+
+
+def extras(kf, Event, peaks):
+    """Other BASELINE configs, same timing rules (>=3 warm-ups, CUDA events, inputs rotated through > L2)."""
+    rng = np.random.default_rng(1234)
+    res = {}
+    N = 4096
+    nsets = 4
+    A = [kf.from_numpy(rng.uniform(-10, 10, (N, N)).astype(np.float32), 0) for _ in range(nsets)]
+    B = [kf.from_numpy(rng.uniform(-10, 10, (N, N)).astype(np.float32), 0) for _ in range(nsets)]
+
+    def t(fn, iters=30, warm=5):
+        for i in range(warm):
+            fn(i % nsets)
+        e0, e1 = Event(), Event()
+        e0.record()
+        for i in range(iters):
+            fn(i % nsets)
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_ms(e1) / iters
+
+    nb = N * N * 4
+    hbm = peaks["hbm_gbs"]
+
+    def mem(name, fn, bytes_alg, **kw):
+        ms = t(fn, **kw)
+        gbs = bytes_alg / ms / 1e6
+        res[name] = {"ms": round(ms, 5), "GB/s": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm, 4), "algorithmic_bytes": bytes_alg}
+
+    mem("c1_add_fp32_4096", lambda i: A[i] + B[i], 3 * nb)
+    mem("c1_mul_fp32_4096", lambda i: A[i] * B[i], 3 * nb)
+    mem("c1_sum_dim0", lambda i: A[i].sum(0), nb + N * 4)
+    mem("c1_sum_dim1", lambda i: A[i].sum(1), nb + N * 4)
+    mem("c1_mean_dim0", lambda i: A[i].mean(0), nb + N * 4)
+    mem("c1_mean_dim1", lambda i: A[i].mean(1), nb + N * 4)
+    mem("c1_permute_contiguous", lambda i: A[i].permute(1, 0).contiguous(), 2 * nb)
+    del A, B
+    # C4 top-k at reduced row count (8192 x 32768 fp32 = 1 GiB > L2; full 65536 rows is the same kernel, 8x longer)
+    rows, cols, k = 8192, 32768, 64
+    X = kf.from_numpy(rng.uniform(-1e5, 1e5, (rows, cols)).astype(np.float32), 0)
+    mem("c4_topk64_8192x32768", lambda i: X.topk(k, 1, True), rows * cols * 4 + rows * k * 12, iters=5, warm=3)
+    del X
+    # C3 causal attention forward bf16 B=8 H=32 S=4096 D=128
+    Bq, H, S, D = 8, 32, 4096, 128
+    q = kf.empty([Bq, H, S, D], kf.bfloat16, 0); q.fill_(0.05)
+    kk = kf.empty([Bq, H, S, D], kf.bfloat16, 0); kk.fill_(0.03)
+    v = kf.empty([Bq, H, S, D], kf.bfloat16, 0); v.fill_(0.5)
+    ms = t(lambda i: kf.causal_attention(q, kk, v), iters=5, warm=3)
+    fl = 4.0 * Bq * H * S * S * D / 2
+    res["c3_attention_fwd_bf16"] = {"ms": round(ms, 4), "TFLOP/s": round(fl / ms / 1e9, 1), "frac_of_tensor_peak": round(fl / ms / 1e9 / peaks["bf16_tflops"], 4)}
+    return res
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    n = N_GEMM
+    rng = np.random.default_rng(1234)
+    flops = 2.0 * n * n * n
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    try:
+        sys.path.insert(0, ref_dir)
+        import kfunca as ref  # the unmodified reference build (resets the device on import, launcher_cuda.h:289)
+
+        a = rng.uniform(-1, 1, (n, n)).astype(np.float32)
+        b = rng.uniform(-1, 1, (n, n)).astype(np.float32)
+
+        def step():  # the reference's own public API, host buffers in, host buffer out
+            out = ref.gemm(ref.from_numpy(a, 0), ref.from_numpy(b, 0), 1.0, 0.0)
+            return out.numpy()
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            step()
+        steps = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        dt = (time.perf_counter() - t0) / steps
+        val = flops / dt / 1e12
+        line = {"impl": "reference", "metric": "bf16 matmul TFLOPS (kfunca gemm, M=N=K=8192)", "value": round(val, 3), "unit": "TFLOP/s",
+                "n_gpus": 1, "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "matmul M=N=K=8192 through the reference kfunca build on the same GPU, FP32 because the reference has no "
+                                       "16-bit GEMM (gemm_kernel.cu:26-36); host buffers in/out through its own from_numpy/numpy"},
+                "cpu_baseline": {"value": round(val, 3), "unit": "TFLOP/s", "cores": os.cpu_count(), "kind": "reference",
+                                 "sample": "full 8192^3 fp32 gemm via oracle/_ref (CUDA build of the reference, PTX-JIT on sm_100)"},
+                "e2e": {"value": round(val, 3), "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+    except Exception as e:  # reference build not loadable here -> the NumPy oracle port on the host cores
+        why = repr(e)[:120]
+    a = rng.uniform(-1, 1, (1024, n)).astype(np.float32)
+    b = rng.uniform(-1, 1, (n, n)).astype(np.float32)
+    a @ b[:, :256]
+    t0 = time.perf_counter()
+    a @ b
+    dt = time.perf_counter() - t0
+    val = 2.0 * 1024 * n * n / dt / 1e12
+    print(json.dumps({"impl": "reference", "metric": "bf16 matmul TFLOPS (kfunca gemm, M=N=K=8192)", "value": round(val, 4), "unit": "TFLOP/s",
+                      "n_gpus": 1, "steps": 1, "warmup": 1, "ms_per_step": round(dt * 1e3 * 8, 1), "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "NumPy fp32 matmul M-slab 1024 x 8192 x 8192 (oracle port; reference build unavailable: " + why + ")"},
+                      "cpu_baseline": {"value": round(val, 4), "unit": "TFLOP/s", "cores": os.cpu_count(), "kind": "port", "sample": "M-slab 1024"},
+                      "e2e": {"value": round(val, 4), "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

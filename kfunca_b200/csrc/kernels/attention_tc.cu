@@ -220,13 +220,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         mbar_wait(pv_done, (nblk - 1) & 1);
         tc_fence_after();
         const float inv_l = 1.f / l_run;
-        if (m_row < p.Sq) {
-            uint16_t *orow = reinterpret_cast<uint16_t *>(p.out) + ((int64_t)bh * p.Sq + m_row) * D;
+        const bool row_ok = m_row < p.Sq;
+        uint16_t *orow = reinterpret_cast<uint16_t *>(p.out) + ((int64_t)bh * p.Sq + (row_ok ? m_row : 0)) * D;
 #pragma unroll 1
-            for (int c = 0; c < D / 32; ++c) {
-                uint32_t orr[32];
-                tmem_ld32(lane_addr + O_COL + (uint32_t)(c * 32), orr);
-                tmem_ld_wait();
+        for (int c = 0; c < D / 32; ++c) {
+            uint32_t orr[32];
+            tmem_ld32(lane_addr + O_COL + (uint32_t)(c * 32), orr);  // .sync.aligned: every lane takes part, only the stores are predicated
+            tmem_ld_wait();
+            if (row_ok) {
                 uint4 *dst = reinterpret_cast<uint4 *>(orow + c * 32);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -237,10 +238,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                     dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
-            if (p.lse) p.lse[(int64_t)bh * p.Sq + m_row] = (m_run + log2f(l_run)) * 0.6931471805599453f;
-        } else {
-            // rows past Sq: still drain the TMEM loads' ordering requirements (nothing to store)
         }
+        if (row_ok && p.lse) p.lse[(int64_t)bh * p.Sq + m_row] = (m_run + log2f(l_run)) * 0.6931471805599453f;
     }
     tc_fence_before();
     __syncthreads();

@@ -32,7 +32,8 @@ def test_causal_attention_fp32(shape):  # ref: test/test_nn.py:11-33 (same tuple
     q, k, v = qkv(*shape, lo=-10, hi=10)
     out = kf.causal_attention(g(q), g(k), g(v))
     assert out.sizes() == list(q.shape) and out.dtype() == kf.float
-    np.testing.assert_allclose(out.numpy(), O.causal_attention(q, k, v), rtol=1e-4, atol=1e-4)
+    # U(-10,10) gives logits with sigma ~33 (near one-hot softmax): the reference's own tolerance (test/common.py:6-11)
+    np.testing.assert_allclose(out.numpy(), O.causal_attention(q, k, v), rtol=1e-3, atol=1e-3)
 
 
 def test_causal_attention_fp32_tight_and_fp64():

@@ -2,15 +2,17 @@
 // The reference's forward is fp32 scalar-FMA only and walks every KV block (src/device/utils/causal_attention.h:73-208;
 // SURVEY F2); this kernel is its B200-native replacement for the 16-bit dtypes the north star asks for.
 //
-// One CTA = 128 query rows of one (batch, head); KV consumed in blocks of 128 keys up to the diagonal.
-//   warp 0    : TMA producer (Q once; K_j, V_j per block; 128B-swizzled tiles)
-//   warp 1    : MMA issuer   S = Q K_j^T  (128x128xD, both operands K-major in smem, fp32 accumulator in TMEM)
-//                            O += P V_j   (128xDx128, P read from TENSOR MEMORY, V MN-major in smem)
-//   warps 2-5 : softmax      thread = query row: tcgen05.ld S, online max/sum in the exp2 domain, P (16-bit)
-//                            written back over S in TMEM (tcgen05.st), O rescaled in TMEM when the row max moved,
-//                            final 1/l scaling + 16-byte global stores + row LSE.
-// TMEM budget is 256 columns (S/P 128 + O D) and shared memory < 100 KB so that TWO CTAs share an SM:
-// while one CTA is in its softmax phase the other one keeps the tensor pipe busy.
+// One CTA = a PAIR of 128-row query tiles of one (batch, head); KV consumed in blocks of 128 keys up to each tile's diagonal.
+//   warp 9    : TMA producer (Q tiles once; K_j, V_j through a 4-slot ring; 128B-swizzled tiles)
+//   warp 8    : MMA issuer   S_t = Q_t K_j^T  (128x128xD, both operands K-major in smem, fp32 accumulator in TMEM)
+//                            O_t += P_t V_j   (128xDx128, P read from TENSOR MEMORY, V MN-major in smem)
+//               issue order  S_0, S_1, then per block { P_0 V + next S_0 ; P_1 V + next S_1 } so the tensor pipe works on
+//               one tile while the softmax warps of the other tile run (ping-pong).
+//   warps 0-3 / 4-7 : softmax of tile 0 / 1.  thread = query row: one tcgen05.ld of the whole S row (128 fp32 registers),
+//               max, exp2 in packed fp32x2 FMAs, P (16-bit) written back over S in TMEM (tcgen05.st).  The running max is
+//               LAZY: it only moves (and O, l are only rescaled) when the row max grew by more than 2^8, which is exact
+//               because the final 1/l normalisation uses the same reference.  Final 1/l scaling + 16-byte stores + row LSE.
+// TMEM: 512 columns = S_0 | S_1 | O_0 | O_1.  Shared memory: 2 Q tiles + 4 K/V slots (192 KB at D = 128), one CTA per SM.
 #include <cmath>
 #include <cstdlib>
 
@@ -20,14 +22,16 @@
 namespace kf {
 using namespace tc;
 
-constexpr int FA_BQ = 128, FA_BKV = 128, FA_THREADS = 192;
+constexpr int FA_BQ = 128, FA_BKV = 128;
+constexpr int FA_THREADS = 320;  // warps 0-3 softmax(tile 0), 4-7 softmax(tile 1), 8 MMA issuer, 9 TMA producer
+constexpr int FA_NSTAGE = 4;     // K/V ring slots (K_0, V_0, K_1, V_1, ... in consumption order)
 
 struct AttnTcParams {
     int64_t BH, Sq, Skv;
     void *out;
     float *lse;
     float scale_log2;  // softmax scale * log2(e)
-    int nq;            // query blocks per (b, h)
+    int npairs;        // 256-row query pairs per (b, h)
     int is_bf16;
 };
 
@@ -52,198 +56,267 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, int is_bf16) {
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// One CTA = two 128-row query tiles (a 256-row "pair") of one (batch, head); the two tiles ping-pong on the
+// tensor pipe: while softmax warps work on S of tile t, the MMA warp runs P V + the next Q K^T of tile 1-t.
 template <int D>
-__global__ void __launch_bounds__(FA_THREADS, 2)
+__global__ void __launch_bounds__(FA_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                    const __grid_constant__ CUtensorMap tmap_v, const AttnTcParams p) {
     constexpr int ATOMS = D / 64;              // 64-element (128 B) swizzle atoms along the head dimension
     constexpr int TILE_BYTES = 128 * D * 2;    // one 128 x D 16-bit tile
     constexpr int ATOM_BYTES = 128 * 128;      // 128 rows x 128 B
-    constexpr uint32_t TMEM_COLS = 256;
-    constexpr uint32_t O_COL = 128;
+    constexpr uint32_t TMEM_COLS = 512;        // S0 | S1 | O0 | O1 (P_t aliases the first 64 columns of S_t)
+    constexpr uint32_t O_COL = 256;
+    constexpr int NS = FA_NSTAGE;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    unsigned char *sQ = smem, *sK = smem + TILE_BYTES, *sV = smem + 2 * TILE_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 3 * TILE_BYTES);
-    uint64_t *q_full = bars + 0, *k_full = bars + 1, *v_full = bars + 2, *k_empty = bars + 3, *s_full = bars + 4, *p_full = bars + 5,
-             *pv_done = bars + 6;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+    unsigned char *sQ = smem;                    // 2 tiles
+    unsigned char *sKV = smem + 2 * TILE_BYTES;  // NS tiles
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (2 + NS) * TILE_BYTES);
+    uint64_t *q_full = bars + 0;
+    uint64_t *kv_full = bars + 1, *kv_empty = bars + 1 + NS;
+    uint64_t *s_full = bars + 1 + 2 * NS;  // [2]
+    uint64_t *p_full = s_full + 2;         // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(p_full + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bh = blockIdx.x / p.nq;
-    const int qb = p.nq - 1 - (blockIdx.x % p.nq);  // heaviest (longest KV range) query blocks first
-    const int q0 = qb * FA_BQ;
-    const int kv_end = (int)min((int64_t)p.Skv, (int64_t)q0 + FA_BQ);
-    const int nblk = (kv_end + FA_BKV - 1) / FA_BKV;
+    const int bh = blockIdx.x / p.npairs;
+    const int pr = p.npairs - 1 - (blockIdx.x % p.npairs);  // heaviest (longest KV range) pairs first
+    const int q0 = pr * 2 * FA_BQ;
+    int nblk[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int64_t q0t = (int64_t)q0 + t * FA_BQ;
+        const int64_t kv_end = min((int64_t)p.Skv, q0t + FA_BQ);
+        nblk[t] = q0t < p.Sq ? (int)((kv_end + FA_BKV - 1) / FA_BKV) : 0;
+    }
+    const int nmax = max(nblk[0], nblk[1]);
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 9 && lane == 0) {
         prefetch_tmap(&tmap_q);
         prefetch_tmap(&tmap_k);
         prefetch_tmap(&tmap_v);
         mbar_init(q_full, 1);
-        mbar_init(k_full, 1);
-        mbar_init(v_full, 1);
-        mbar_init(k_empty, 1);
-        mbar_init(s_full, 1);
-        mbar_init(p_full, 4);
-        mbar_init(pv_done, 1);
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&kv_empty[s], 1);
+        }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(&s_full[t], 1);
+            mbar_init(&p_full[t], 4);
+        }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 8) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == 9) {
+        // ===================================================== TMA producer
         if (lane == 0) {
-            mbar_arrive_expect_tx(q_full, TILE_BYTES);
+            const int ntile_q = nblk[1] > 0 ? 2 : 1;
+            mbar_arrive_expect_tx(q_full, ntile_q * TILE_BYTES);
+            for (int t = 0; t < ntile_q; ++t)
 #pragma unroll
-            for (int a = 0; a < ATOMS; ++a) tma_load_3d(sQ + a * ATOM_BYTES, &tmap_q, q_full, a * 64, q0, bh);
-            for (int j = 0; j < nblk; ++j) {
-                const int kv0 = j * FA_BKV;
-                mbar_wait(k_empty, (j & 1) ^ 1);
-                mbar_arrive_expect_tx(k_full, TILE_BYTES);
+                for (int a = 0; a < ATOMS; ++a) tma_load_3d(sQ + t * TILE_BYTES + a * ATOM_BYTES, &tmap_q, q_full, a * 64, q0 + t * FA_BQ, bh);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int i = 0; i < 2 * nmax; ++i) {  // K_0, V_0, K_1, V_1, ...
+                const int kv0 = (i >> 1) * FA_BKV;
+                const CUtensorMap *tm = (i & 1) ? &tmap_v : &tmap_k;
+                mbar_wait(&kv_empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&kv_full[s], TILE_BYTES);
 #pragma unroll
-                for (int a = 0; a < ATOMS; ++a) tma_load_3d(sK + a * ATOM_BYTES, &tmap_k, k_full, a * 64, kv0, bh);
-                mbar_wait(pv_done, (j & 1) ^ 1);  // V tile free once P V_{j-1} has completed
-                mbar_arrive_expect_tx(v_full, TILE_BYTES);
-#pragma unroll
-                for (int a = 0; a < ATOMS; ++a) tma_load_3d(sV + a * ATOM_BYTES, &tmap_v, v_full, a * 64, kv0, bh);
+                for (int a = 0; a < ATOMS; ++a) tma_load_3d(sKV + s * TILE_BYTES + a * ATOM_BYTES, tm, &kv_full[s], a * 64, kv0, bh);
+                if (++s == NS) {
+                    s = 0;
+                    ph ^= 1;
+                }
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
+    } else if (warp == 8) {
+        // ===================================================== MMA issuer
         if (lane == 0) {
             const int fmt = p.is_bf16 ? 1 : 0;
             const uint32_t idesc_s = make_idesc_f16(fmt, 0, 0, FA_BQ, FA_BKV);
             const uint32_t idesc_pv = make_idesc_f16(fmt, 0, 1, FA_BQ, D);
-            const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-            mbar_wait(q_full, 0);
-            for (int j = 0; j < nblk; ++j) {
-                mbar_wait(k_full, j & 1);
-                if (j > 0) mbar_wait(pv_done, (j - 1) & 1);  // P_{j-1} (aliased with S) consumed, O updated
-                tc_fence_after();
+            const uint32_t q_addr = smem_u32(sQ), kv_addr = smem_u32(sKV);
+            auto issue_s = [&](int t, uint32_t k_addr) {
 #pragma unroll
                 for (int kk = 0; kk < D / 16; ++kk) {
                     const uint32_t off = (uint32_t)((kk >> 2) * ATOM_BYTES + (kk & 3) * 32);
-                    umma_f16(tmem_base, make_sw128_desc(q_addr + off, 0, 1024), make_sw128_desc(k_addr + off, 0, 1024), idesc_s, kk ? 1u : 0u);
+                    umma_f16(tmem_base + (uint32_t)(t * 128), make_sw128_desc(q_addr + t * TILE_BYTES + off, 0, 1024),
+                             make_sw128_desc(k_addr + off, 0, 1024), idesc_s, kk ? 1u : 0u);
                 }
-                umma_commit(k_empty);
-                umma_commit(s_full);
-                mbar_wait(p_full, j & 1);
-                mbar_wait(v_full, j & 1);
-                tc_fence_after();
+            };
+            auto issue_pv = [&](int t, uint32_t v_addr, bool accumulate) {
 #pragma unroll
                 for (int kk = 0; kk < FA_BKV / 16; ++kk) {
                     // A = P from tensor memory: 16 k-values of 16 bits = 8 columns per step;
                     // B = V, MN-major: 16 kv rows = 2 x 1024 B per step, 64-wide d atoms ATOM_BYTES apart
-                    umma_f16_ts(tmem_base + O_COL, tmem_base + (uint32_t)(kk * 8), make_sw128_desc(v_addr + kk * 2048, ATOM_BYTES, 1024), idesc_pv,
-                                (j | kk) ? 1u : 0u);
+                    umma_f16_ts(tmem_base + O_COL + (uint32_t)(t * D), tmem_base + (uint32_t)(t * 128 + kk * 8),
+                                make_sw128_desc(v_addr + kk * 2048, ATOM_BYTES, 1024), idesc_pv, (accumulate || kk) ? 1u : 0u);
                 }
-                umma_commit(pv_done);
+            };
+            int s = 0;
+            uint32_t ph = 0;
+            auto next_slot = [&]() {
+                mbar_wait(&kv_full[s], ph);
+                const int cur = s;
+                if (++s == NS) {
+                    s = 0;
+                    ph ^= 1;
+                }
+                return cur;
+            };
+            mbar_wait(q_full, 0);
+            {
+                const int sk = next_slot();  // K_0
+                tc_fence_after();
+                for (int t = 0; t < 2; ++t)
+                    if (nblk[t] > 0) {
+                        issue_s(t, kv_addr + sk * TILE_BYTES);
+                        umma_commit(&s_full[t]);
+                    }
+                umma_commit(&kv_empty[sk]);
+            }
+            for (int j = 1; j <= nmax; ++j) {
+                const int sv = next_slot();  // V_{j-1}
+                const bool has_k = j < nmax;
+                const int sk = has_k ? next_slot() : 0;  // K_j
+                for (int t = 0; t < 2; ++t) {
+                    if (j - 1 < nblk[t]) {
+                        mbar_wait(&p_full[t], (uint32_t)((j - 1) & 1));
+                        tc_fence_after();
+                        issue_pv(t, kv_addr + sv * TILE_BYTES, j > 1);
+                        if (j < nblk[t]) issue_s(t, kv_addr + sk * TILE_BYTES);
+                        umma_commit(&s_full[t]);
+                    }
+                }
+                umma_commit(&kv_empty[sv]);
+                if (has_k) umma_commit(&kv_empty[sk]);
             }
         }
         __syncwarp();
     } else {
-        const int q = warp & 3;
-        const int r = q * 32 + lane;
-        const int64_t m_row = (int64_t)q0 + r;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        float m_run = -INFINITY, l_run = 0.f;
-        for (int j = 0; j < nblk; ++j) {
-            const int kv0 = j * FA_BKV;
-            const bool need_mask = (kv0 + FA_BKV - 1 > q0) || (kv0 + FA_BKV > p.Skv);
-            mbar_wait(s_full, j & 1);
+        // ===================================================== softmax + epilogue: thread = one query row of tile t
+        const int t = warp >> 2, q = warp & 3;
+        const int n_t = nblk[t];
+        if (n_t > 0) {
+            const int r = q * 32 + lane;
+            const int64_t q0t = (int64_t)q0 + t * FA_BQ;
+            const int64_t m_row = q0t + r;
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+            const uint32_t s_addr = lane_addr + (uint32_t)(t * 128);
+            const uint32_t o_addr = lane_addr + O_COL + (uint32_t)(t * D);
+            const float sc = p.scale_log2;
+            float m_ref = -INFINITY, l_run = 0.f;
+            for (int j = 0; j < n_t; ++j) {
+                const int kv0 = j * FA_BKV;
+                mbar_wait(&s_full[t], (uint32_t)(j & 1));
+                tc_fence_after();
+                uint32_t s[4][32];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) tmem_ld32(s_addr + (uint32_t)(c * 32), s[c]);
+                tmem_ld_wait();
+                if ((kv0 + FA_BKV - 1 > q0t) || (kv0 + FA_BKV > p.Skv)) {  // diagonal / ragged block: mask in registers
+                    const int64_t lim64 = min(m_row, p.Skv - 1) - kv0;     // columns i > lim are masked
+                    const int lim = (int)max((int64_t)-1, min(lim64, (int64_t)127));
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i > lim) s[c][i] = 0xff800000u;  // -inf
+                }
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        mx0 = fmaxf(mx0, __uint_as_float(s[c][i]));
+                        mx1 = fmaxf(mx1, __uint_as_float(s[c][i + 1]));
+                        mx2 = fmaxf(mx2, __uint_as_float(s[c][i + 2]));
+                        mx3 = fmaxf(mx3, __uint_as_float(s[c][i + 3]));
+                    }
+                const float m_new = fmaxf(m_ref, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc);
+                // lazy reference max: only move it (and rescale O, l) when the row max grew by more than 2^8
+                const bool grow = j == 0 ? true : (m_new - m_ref > 8.f);
+                if (j > 0 && __any_sync(0xffffffffu, grow)) {
+                    const float f = grow ? ((m_ref == -INFINITY) ? 0.f : ex2_approx(m_ref - m_new)) : 1.f;
+                    l_run *= f;
+#pragma unroll 1
+                    for (int c = 0; c < D / 32; ++c) {
+                        uint32_t orr[32];
+                        tmem_ld32(o_addr + (uint32_t)(c * 32), orr);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * f);
+                        tmem_st32(o_addr + (uint32_t)(c * 32), orr);
+                    }
+                }
+                if (grow) m_ref = m_new;
+                const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+                const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(-m_use, -m_use);
+                float2 rs2 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < 4; c += 2) {
+                    uint32_t pk[32];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c + h][i]), __uint_as_float(s[c + h][i + 1])), sc2, nm2);
+                            x.x = ex2_approx(x.x);
+                            x.y = ex2_approx(x.y);
+                            rs2 = __fadd2_rn(rs2, x);
+                            pk[h * 16 + (i >> 1)] = pack16(x.x, x.y, p.is_bf16);
+                        }
+                    tmem_st32(s_addr + (uint32_t)(c * 16), pk);
+                }
+                l_run += rs2.x + rs2.y;
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[t]);
+            }
+            // ---- epilogue: O / l -> 16-bit -> global, row LSE
+            mbar_wait(&s_full[t], (uint32_t)(n_t & 1));
             tc_fence_after();
-            // ---- pass 1: row max (scaled to the exp2 domain)
-            float mx = -INFINITY;
+            const float inv_l = 1.f / l_run;
+            const bool row_ok = m_row < p.Sq;
+            uint16_t *orow = reinterpret_cast<uint16_t *>(p.out) + ((int64_t)bh * p.Sq + (row_ok ? m_row : 0)) * D;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t sr[32];
-                tmem_ld32(lane_addr + (uint32_t)(c * 32), sr);
+            for (int c = 0; c < D / 32; ++c) {
+                uint32_t orr[32];
+                tmem_ld32(o_addr + (uint32_t)(c * 32), orr);  // .sync.aligned: every lane takes part, only the stores are predicated
                 tmem_ld_wait();
+                if (row_ok) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(orow + c * 32);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float s = __uint_as_float(sr[i]);
-                    if (need_mask) {
-                        const int64_t n = (int64_t)kv0 + c * 32 + i;
-                        if (n > m_row || n >= p.Skv) s = -INFINITY;
+                    for (int i = 0; i < 4; ++i) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            w[k] = pack16(__uint_as_float(orr[8 * i + 2 * k]) * inv_l, __uint_as_float(orr[8 * i + 2 * k + 1]) * inv_l, p.is_bf16);
+                        dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
                     }
-                    mx = fmaxf(mx, s);
                 }
             }
-            const float m_new = fmaxf(m_run, mx * p.scale_log2);
-            const float corr = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
-            // ---- pass 2: p = exp2(s * c - m), written back over S as packed 16-bit pairs
-            float rs = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t sr[32];
-                tmem_ld32(lane_addr + (uint32_t)(c * 32), sr);
-                tmem_ld_wait();
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float s0 = __uint_as_float(sr[i]), s1 = __uint_as_float(sr[i + 1]);
-                    float p0 = exp2f(fmaf(s0, p.scale_log2, -m_new)), p1 = exp2f(fmaf(s1, p.scale_log2, -m_new));
-                    if (need_mask) {
-                        const int64_t n = (int64_t)kv0 + c * 32 + i;
-                        if (n > m_row || n >= p.Skv) p0 = 0.f;
-                        if (n + 1 > m_row || n + 1 >= p.Skv) p1 = 0.f;
-                    }
-                    rs += p0 + p1;
-                    pk[i >> 1] = pack16(p0, p1, p.is_bf16);
-                }
-                tmem_st16(lane_addr + (uint32_t)(c * 16), pk);
-            }
-            l_run = l_run * corr + rs;
-            m_run = m_new;
-            // ---- rescale the running O accumulator when some row of this warp moved its max
-            if (j > 0 && __any_sync(0xffffffffu, corr != 1.f)) {
-#pragma unroll 1
-                for (int c = 0; c < D / 32; ++c) {
-                    uint32_t orr[32];
-                    tmem_ld32(lane_addr + O_COL + (uint32_t)(c * 32), orr);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * corr);
-                    tmem_st32(lane_addr + O_COL + (uint32_t)(c * 32), orr);
-                }
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(p_full);
+            if (row_ok && p.lse) p.lse[(int64_t)bh * p.Sq + m_row] = (m_ref + log2f(l_run)) * 0.6931471805599453f;
         }
-        // ---- epilogue: O / l -> 16-bit -> global, row LSE
-        mbar_wait(pv_done, (nblk - 1) & 1);
-        tc_fence_after();
-        const float inv_l = 1.f / l_run;
-        const bool row_ok = m_row < p.Sq;
-        uint16_t *orow = reinterpret_cast<uint16_t *>(p.out) + ((int64_t)bh * p.Sq + (row_ok ? m_row : 0)) * D;
-#pragma unroll 1
-        for (int c = 0; c < D / 32; ++c) {
-            uint32_t orr[32];
-            tmem_ld32(lane_addr + O_COL + (uint32_t)(c * 32), orr);  // .sync.aligned: every lane takes part, only the stores are predicated
-            tmem_ld_wait();
-            if (row_ok) {
-                uint4 *dst = reinterpret_cast<uint4 *>(orow + c * 32);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        w[k] = pack16(__uint_as_float(orr[8 * i + 2 * k]) * inv_l, __uint_as_float(orr[8 * i + 2 * k + 1]) * inv_l, p.is_bf16);
-                    dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-            }
-        }
-        if (row_ok && p.lse) p.lse[(int64_t)bh * p.Sq + m_row] = (m_run + log2f(l_run)) * 0.6931471805599453f;
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 8) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
@@ -261,16 +334,16 @@ static void launch_fwd_tc(const AttnPlan &a) {
     p.out = a.out;
     p.lse = reinterpret_cast<float *>(a.lse);
     p.scale_log2 = (float)(1.4426950408889634 / std::sqrt((double)D));
-    p.nq = (int)((a.Sq + FA_BQ - 1) / FA_BQ);
+    p.npairs = (int)((a.Sq + 2 * FA_BQ - 1) / (2 * FA_BQ));
     p.is_bf16 = bf16;
-    constexpr int SMEM = 3 * 128 * D * 2 + 256 + 1024;
+    constexpr int SMEM = (2 + FA_NSTAGE) * 128 * D * 2 + 256 + 1024;
     auto kern = attn_fwd_tc_kernel<D>;
     static bool attr_done = false;
     if (!attr_done) {
         KF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr_done = true;
     }
-    const int64_t grid = a.BH * p.nq;
+    const int64_t grid = a.BH * p.npairs;
     KF_CHECK(grid < (int64_t)0x7FFFFFFF);
     kern<<<(unsigned)grid, FA_THREADS, SMEM, rt.stream()>>>(tq, tk, tv, p);
     rt.post_launch("attn_fwd_tc_kernel");

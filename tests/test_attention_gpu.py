@@ -65,6 +65,18 @@ def test_causal_attention_tc_16bit(dt, shape):
     np.testing.assert_allclose(lse.numpy(), lse_exact, rtol=1e-2, atol=1e-2)
 
 
+@pytest.mark.parametrize("dt", ["bf16", "fp16"])
+@pytest.mark.parametrize("shape", [(1, 2, 512, 512, 128), (1, 2, 700, 900, 64), (2, 1, 257, 257, 128)])
+def test_causal_attention_tc_large_logits(dt, shape):
+    """wide logit range (sigma ~ 10 in the exp2 domain): the lazily-moved reference max must rescale O and l"""
+    q, k, v = (to16(t, dt) for t in qkv(*shape, lo=-4.0, hi=4.0))
+    out, lse = kf.causal_attention_fwd(g(q), g(k), g(v))
+    exact, lse_exact = O.causal_attention(q, k, v, return_lse=True)
+    got = out.float().numpy().astype(np.float64)
+    assert np.all(np.abs(got - exact) <= 2e-2 * np.abs(exact) + 3e-2), float(np.abs(got - exact).max())
+    np.testing.assert_allclose(lse.numpy(), lse_exact, rtol=1e-2, atol=2e-2)
+
+
 def test_attention_16bit_odd_head_dim_uses_simt():
     q, k, v = (to16(t, "bf16") for t in qkv(1, 2, 40, 40, 24))
     got = kf.causal_attention(g(q), g(k), g(v)).float().numpy()

@@ -1,0 +1,59 @@
+"""Profiling workload: one pass over each hot-path family at its BASELINE size (for `ncu`; never a bench number).
+
+  python tools/prof_ops.py [family ...]      families: ew reduce permute topk gemm attn attn_bwd
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+import kfunca_b200 as kf
+
+fams = set(sys.argv[1:]) or {"ew", "reduce", "permute", "topk", "gemm", "attn"}
+rng = np.random.default_rng(1234)
+REPS = int(os.environ.get("KF_PROF_REPS", "2"))
+
+if fams & {"ew", "reduce", "permute"}:
+    N = 4096
+    a = kf.from_numpy(rng.uniform(-10, 10, (N, N)).astype(np.float32), 0)
+    b = kf.from_numpy(rng.uniform(-10, 10, (N, N)).astype(np.float32), 0)
+    for _ in range(REPS):
+        if "ew" in fams:
+            a + b
+            a * b
+        if "reduce" in fams:
+            a.sum(0)
+            a.sum(1)
+            a.mean(0)
+            a.mean(1)
+            a.view(-1).sum(0)
+        if "permute" in fams:
+            a.permute(1, 0).contiguous()
+    del a, b
+if "topk" in fams:
+    x = kf.from_numpy(rng.uniform(-1e5, 1e5, (8192, 32768)).astype(np.float32), 0)
+    for _ in range(REPS):
+        x.topk(64, 1, True)
+    del x
+if "gemm" in fams:
+    n = 8192
+    A = kf.empty([n, n], kf.bfloat16, 0)
+    B = kf.empty([n, n], kf.bfloat16, 0)
+    A.fill_(0.01)
+    B.fill_(0.02)
+    for _ in range(REPS):
+        kf.gemm(A, B, 1.0, 0.0)
+    del A, B
+if fams & {"attn", "attn_bwd"}:
+    Bq, H, S, D = (8, 32, 4096, 128) if "KF_PROF_SMALL" not in os.environ else (1, 4, 4096, 128)
+    q = kf.empty([Bq, H, S, D], kf.bfloat16, 0)
+    k = kf.empty([Bq, H, S, D], kf.bfloat16, 0)
+    v = kf.empty([Bq, H, S, D], kf.bfloat16, 0)
+    q.fill_(0.05)
+    k.fill_(0.03)
+    v.fill_(0.5)
+    for _ in range(REPS):
+        o = kf.causal_attention(q, k, v)
+kf.synchronize()
+print("prof_ops done")

@@ -1,19 +1,23 @@
 // sm_100a sum / mean over one axis of a dense [outer, R, inner] tensor (keepdim handled by the caller).
 // Replaces the reference's gpu_reduce_kernel / ReduceOp family (src/device/utils/tensor_reduce.h:122-1083;
 // functors src/device/reduce_ops_kernel.cu:6-59).  Design:
-//   inner == 1 (row reduce)   : many short rows -> one warp per row, 128-bit loads, shuffle tree;
-//                               few long rows   -> row split over S CTAs; a thread-block CLUSTER of up to
+//   inner == 1 (row reduce)   : many rows -> W in {1,2,4,8} warps per row (8 / W rows per CTA), 128-bit streaming
+//                               loads with 8 in flight per lane, shuffle tree;
+//                               few long rows -> row split over S CTAs; a thread-block CLUSTER of up to
 //                               8 CTAs folds its partials through distributed shared memory (DSMEM), so
 //                               only S/8 partials per row ever touch HBM (none when S <= 8).
 //   inner  > 1 (column reduce): lanes run along `inner` (coalesced, 128-bit), warps + cluster CTAs split R,
 //                               combined through shared memory and DSMEM.
-// No global semaphores / atomics (the reference's un-zeroed semaphore hazard, SURVEY F10, cannot occur) and
+// Every reduction is ONE launch: when an output needs more than one cluster, the cluster partials go to a
+// scratch buffer and the last cluster to arrive (library-owned, zero-initialised, self-resetting counters —
+// the reference's un-zeroed semaphore hazard, SURVEY F10, cannot occur) folds them in cluster order, so
 // the summation order is fixed by the launch geometry => deterministic run to run.
 // Accumulation: fp32 for fp16/bf16/fp32 (documented deviation from the reference's accumulate-in-input-dtype,
 // SURVEY F6), fp64 for fp64, int64 for integers/bool (truncation on store == the reference's wrap-around).
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "ew_common.cuh"
@@ -24,14 +28,15 @@ namespace kf {
 
 struct ReduceArgs {
     const void *in;
-    void *out;       // final output (Tout) or partial buffer (A)
-    int64_t rows;    // row kernels: number of rows; col kernels: outer
+    void *out;          // final output (Tout)
+    void *partial;      // [groups][nparts][...] accumulator-typed partials (split kernels, nparts > 1)
+    uint32_t *counter;  // one self-resetting arrival counter per output group (split kernels, nparts > 1)
+    int64_t rows;       // row kernels: number of rows; col kernels: outer
     int64_t R;
     int64_t inner;
-    int64_t chunk;   // elements (rows) of R handled by one CTA
-    int S;           // splits of R
-    int C;           // cluster size along the split
-    int write_partial;
+    int64_t chunk;      // elements (rows) of R handled by one CTA
+    int S;              // splits of R
+    int C;              // cluster size along the split
     int is_mean;
     double factor_f;
     int64_t factor_i;
@@ -51,34 +56,104 @@ __device__ __forceinline__ A warp_sum(A v) {
     return v;
 }
 
-// ------------------------------------------------------------------ rows: one warp per row
-template <typename Tin, typename Tout, typename A, int VEC>
-__global__ void __launch_bounds__(256) reduce_rows_warp_kernel(const ReduceArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= a.rows) return;
-    const Tin *__restrict__ p = reinterpret_cast<const Tin *>(a.in) + row * a.R;
-    A acc = A(0);
-    if constexpr (VEC > 1) {
-        const int64_t nv = a.R / VEC;
-        const Pack<Tin, VEC> *pv = reinterpret_cast<const Pack<Tin, VEC> *>(p);
-#pragma unroll 4
-        for (int64_t i = lane; i < nv; i += 32) {
-            Pack<Tin, VEC> pk = pv[i];
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) acc += cvt_in<A>(pk.v[j]);
-        }
+// streaming 16-byte load that does not allocate in L1 (every input byte is read exactly once)
+template <typename T, int VEC>
+__device__ __forceinline__ Pack<T, VEC> ld_stream(const Pack<T, VEC> *p) {
+    if constexpr (sizeof(Pack<T, VEC>) == 16) {
+        uint4 r;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+        Pack<T, VEC> out;
+        *reinterpret_cast<uint4 *>(&out) = r;
+        return out;
     } else {
-#pragma unroll 4
-        for (int64_t i = lane; i < a.R; i += 32) acc += cvt_in<A>(p[i]);
+        return *p;
     }
-    acc = warp_sum(acc);
-    if (lane == 0) reinterpret_cast<Tout *>(a.out)[row] = cvt_out<Tout, A>(finalize(acc, a));
 }
 
-// ------------------------------------------------------------------ rows: CTA (x cluster) per row
+// sum of nv vectors starting at pv[first], stride `step` vectors, 8 independent loads in flight per thread
+template <typename Tin, typename A, int VEC>
+__device__ __forceinline__ A strided_vec_sum(const Pack<Tin, VEC> *pv, int64_t first, int64_t step, int64_t nv) {
+    A acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = A(0);
+    int64_t i = first;
+    for (; i + 7 * step < nv; i += 8 * step) {
+        Pack<Tin, VEC> pk[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) pk[u] = ld_stream<Tin, VEC>(pv + i + u * step);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[j] += cvt_in<A>(pk[u].v[j]);
+    }
+    for (; i < nv; i += step) {
+        Pack<Tin, VEC> pk = ld_stream<Tin, VEC>(pv + i);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] += cvt_in<A>(pk.v[j]);
+    }
+    A tot = A(0);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) tot += acc[j];
+    return tot;
+}
+
+// ------------------------------------------------------------------ rows: W warps per row, 8 / W rows per CTA
+template <typename Tin, typename Tout, typename A, int VEC, int W>
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const ReduceArgs a) {
+    __shared__ A part[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wr = warp % W;                                  // this warp's slot inside its row
+    const int64_t row = (int64_t)blockIdx.x * (8 / W) + warp / W;
+    A acc = A(0);
+    if (row < a.rows) {
+        const Tin *__restrict__ p = reinterpret_cast<const Tin *>(a.in) + row * a.R;
+        if constexpr (VEC > 1) {
+            acc = strided_vec_sum<Tin, A, VEC>(reinterpret_cast<const Pack<Tin, VEC> *>(p), wr * 32 + lane, W * 32, a.R / VEC);
+        } else {
+#pragma unroll 4
+            for (int64_t i = wr * 32 + lane; i < a.R; i += W * 32) acc += cvt_in<A>(p[i]);
+        }
+    }
+    acc = warp_sum(acc);
+    if constexpr (W == 1) {
+        if (lane == 0 && row < a.rows) reinterpret_cast<Tout *>(a.out)[row] = cvt_out<Tout, A>(finalize(acc, a));
+    } else {
+        if (lane == 0) part[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x < 8 / W) {
+            const int64_t r = (int64_t)blockIdx.x * (8 / W) + threadIdx.x;
+            if (r < a.rows) {
+                A v = A(0);
+#pragma unroll
+                for (int k = 0; k < W; ++k) v += part[threadIdx.x * W + k];
+                reinterpret_cast<Tout *>(a.out)[r] = cvt_out<Tout, A>(finalize(v, a));
+            }
+        }
+    }
+}
+
+// Cross-CTA finish shared by the split kernels.  Cluster rank 0 of each cluster has the cluster's partial in
+// `mine` (thread-strided over `width` slots).  With more than one cluster per output group the partials go to
+// global memory and the LAST cluster to arrive (self-resetting counter) folds them in cluster order — the
+// summation order is fixed, so the result is deterministic.  Returns true for the threads that must store.
+template <typename A>
+__device__ __forceinline__ bool publish_and_elect(const ReduceArgs &a, A *group_partials, int part_idx, int nparts, int width, const A *mine_smem,
+                                                  uint32_t *counter) {
+    __shared__ uint32_t s_ticket;
+    for (int t = threadIdx.x; t < width; t += blockDim.x) group_partials[(int64_t)part_idx * width + t] = mine_smem[t];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(counter, 1u);
+    __syncthreads();
+    if (s_ticket != (uint32_t)(nparts - 1)) return false;
+    if (threadIdx.x == 0) *counter = 0;  // re-arm for the next launch (stream-ordered)
+    __threadfence();
+    return true;
+}
+
+// ------------------------------------------------------------------ rows: few long rows, R split over S CTAs
 template <typename Tin, typename Tout, typename A, int VEC>
-__global__ void __launch_bounds__(256) reduce_rows_block_kernel(const ReduceArgs a) {
+__global__ void __launch_bounds__(256) reduce_rows_split_kernel(const ReduceArgs a) {
     __shared__ A warp_part[8];
     __shared__ A cta_val;
     const int s = blockIdx.x;
@@ -89,15 +164,8 @@ __global__ void __launch_bounds__(256) reduce_rows_block_kernel(const ReduceArgs
     const Tin *__restrict__ p = reinterpret_cast<const Tin *>(a.in) + row * a.R;
     A acc = A(0);
     if (lo < hi) {
-        if constexpr (VEC > 1) {
-            const Pack<Tin, VEC> *pv = reinterpret_cast<const Pack<Tin, VEC> *>(p + lo);
-            const int64_t nv = (hi - lo) / VEC;  // host guarantees chunk % VEC == 0 and R % VEC == 0
-#pragma unroll 4
-            for (int64_t i = threadIdx.x; i < nv; i += 256) {
-                Pack<Tin, VEC> pk = pv[i];
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) acc += cvt_in<A>(pk.v[j]);
-            }
+        if constexpr (VEC > 1) {  // host guarantees chunk % VEC == 0 and R % VEC == 0
+            acc = strided_vec_sum<Tin, A, VEC>(reinterpret_cast<const Pack<Tin, VEC> *>(p + lo), threadIdx.x, 256, (hi - lo) / VEC);
         } else {
 #pragma unroll 4
             for (int64_t i = lo + threadIdx.x; i < hi; i += 256) acc += cvt_in<A>(p[i]);
@@ -111,24 +179,37 @@ __global__ void __launch_bounds__(256) reduce_rows_block_kernel(const ReduceArgs
         v = warp_sum(v);
         if (threadIdx.x == 0) cta_val = v;
     }
-    A total;
     if (a.C > 1) {
         cg::cluster_group cluster = cg::this_cluster();
         cluster.sync();  // every CTA's cta_val is written and visible cluster-wide
         if (cluster.block_rank() == 0 && threadIdx.x == 0) {
-            total = A(0);
+            A total = A(0);
             for (int r = 0; r < a.C; ++r) total += *cluster.map_shared_rank(&cta_val, r);  // DSMEM reads
+            cta_val = total;
         }
         cluster.sync();  // peers keep their shared memory alive until rank 0 has read it
         if (cluster.block_rank() != 0) return;
-    } else {
+    }
+    __syncthreads();
+    const int nparts = a.S / a.C;
+    if (nparts > 1) {
+        A *gp = reinterpret_cast<A *>(a.partial) + row * nparts;
+        if (!publish_and_elect<A>(a, gp, s / a.C, nparts, 1, &cta_val, a.counter + row)) return;
+        // fixed-shape parallel fold of the cluster partials: thread t owns partials t, t+256, ...; shuffle tree; 8 warp sums
+        A v = A(0);
+        for (int k = threadIdx.x; k < nparts; k += 256) v += __ldcg(gp + k);
+        v = warp_sum(v);
+        if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = v;
         __syncthreads();
-        total = cta_val;
+        if (threadIdx.x == 0) {
+            A total = A(0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) total += warp_part[k];
+            cta_val = total;
+        }
+        __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        if (a.write_partial) reinterpret_cast<A *>(a.out)[row * (a.S / a.C) + s / a.C] = total;
-        else reinterpret_cast<Tout *>(a.out)[row] = cvt_out<Tout, A>(finalize(total, a));
-    }
+    if (threadIdx.x == 0) reinterpret_cast<Tout *>(a.out)[row] = cvt_out<Tout, A>(finalize(cta_val, a));
 }
 
 // ------------------------------------------------------------------ columns
@@ -147,9 +228,18 @@ __global__ void __launch_bounds__(256) reduce_cols_kernel(const ReduceArgs a) {
     for (int j = 0; j < VEC; ++j) acc[j] = A(0);
     if (col < a.inner) {
         const Tin *__restrict__ p = reinterpret_cast<const Tin *>(a.in) + o * a.R * a.inner + col;
-#pragma unroll 4
-        for (int64_t r = lo + w; r < hi; r += 8) {
-            Pack<Tin, VEC> pk = *reinterpret_cast<const Pack<Tin, VEC> *>(p + r * a.inner);
+        int64_t r = lo + w;
+        for (; r + 56 < hi; r += 64) {  // 8 independent 16-byte loads in flight per thread
+            Pack<Tin, VEC> pk[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) pk[u] = ld_stream<Tin, VEC>(reinterpret_cast<const Pack<Tin, VEC> *>(p + (r + 8 * u) * a.inner));
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) acc[j] += cvt_in<A>(pk[u].v[j]);
+        }
+        for (; r < hi; r += 8) {
+            Pack<Tin, VEC> pk = ld_stream<Tin, VEC>(reinterpret_cast<const Pack<Tin, VEC> *>(p + r * a.inner));
 #pragma unroll
             for (int j = 0; j < VEC; ++j) acc[j] += cvt_in<A>(pk.v[j]);
         }
@@ -169,23 +259,57 @@ __global__ void __launch_bounds__(256) reduce_cols_kernel(const ReduceArgs a) {
         cluster.sync();
         if (cluster.block_rank() == 0) {
             for (int t = threadIdx.x; t < 32 * VEC; t += 256) {
-                A v = part[0][t];
-                for (int r = 1; r < a.C; ++r) v += cluster.map_shared_rank(&part[0][0], r)[t];
-                part[0][t] = v;
+                A v0 = part[0][t], v1 = A(0), v2 = A(0), v3 = A(0);
+                int r = 1;
+                for (; r + 3 < a.C; r += 4) {  // independent DSMEM reads in flight
+                    v1 += cluster.map_shared_rank(&part[0][0], r)[t];
+                    v2 += cluster.map_shared_rank(&part[0][0], r + 1)[t];
+                    v3 += cluster.map_shared_rank(&part[0][0], r + 2)[t];
+                    v0 += cluster.map_shared_rank(&part[0][0], r + 3)[t];
+                }
+                for (; r < a.C; ++r) v1 += cluster.map_shared_rank(&part[0][0], r)[t];
+                part[0][t] = (v0 + v1) + (v2 + v3);
             }
         }
         cluster.sync();
         if (cluster.block_rank() != 0) return;
-    } else {
-        __syncthreads();
     }
-    for (int t = threadIdx.x; t < 32 * VEC; t += 256) {
-        const int64_t c = (int64_t)blockIdx.x * 32 * VEC + t;
-        if (c < a.inner) {
-            const A v = part[0][t];
-            if (a.write_partial) reinterpret_cast<A *>(a.out)[(o * (a.S / a.C) + s / a.C) * a.inner + c] = v;
-            else reinterpret_cast<Tout *>(a.out)[o * a.inner + c] = cvt_out<Tout, A>(finalize(v, a));
+    __syncthreads();
+    const int nparts = a.S / a.C;
+    const int width = 32 * VEC;
+    if (nparts > 1) {
+        const int64_t group = o * gridDim.x + blockIdx.x;
+        A *gp = reinterpret_cast<A *>(a.partial) + group * nparts * width;
+        if (!publish_and_elect<A>(a, gp, s / a.C, nparts, width, &part[0][0], a.counter + group)) return;
+        // parallel fold: 256 / width thread groups split the partials (fixed assignment => deterministic), 4 loads in flight
+        constexpr int GROUPS = (256 / (32 * VEC)) > 0 ? (256 / (32 * VEC)) : 1;
+        for (int t = threadIdx.x; t < width * GROUPS; t += 256) {
+            const int slot = t % width, g = t / width;
+            A v0 = A(0), v1 = A(0), v2 = A(0), v3 = A(0);
+            int k = g;
+            for (; k + 3 * GROUPS < nparts; k += 4 * GROUPS) {
+                v0 += __ldcg(gp + (int64_t)k * width + slot);
+                v1 += __ldcg(gp + (int64_t)(k + GROUPS) * width + slot);
+                v2 += __ldcg(gp + (int64_t)(k + 2 * GROUPS) * width + slot);
+                v3 += __ldcg(gp + (int64_t)(k + 3 * GROUPS) * width + slot);
+            }
+            for (; k < nparts; k += GROUPS) v0 += __ldcg(gp + (int64_t)k * width + slot);
+            part[g][slot] = (v0 + v1) + (v2 + v3);
         }
+        __syncthreads();
+        if (GROUPS > 1) {
+            for (int t = threadIdx.x; t < width; t += 256) {
+                A v = part[0][t];
+#pragma unroll
+                for (int g = 1; g < GROUPS; ++g) v += part[g][t];
+                part[0][t] = v;
+            }
+            __syncthreads();
+        }
+    }
+    for (int t = threadIdx.x; t < width; t += 256) {
+        const int64_t c = (int64_t)blockIdx.x * width + t;
+        if (c < a.inner) reinterpret_cast<Tout *>(a.out)[o * a.inner + c] = cvt_out<Tout, A>(finalize(part[0][t], a));
     }
 }
 
@@ -205,57 +329,97 @@ static void launch_clustered(K kernel, dim3 grid, dim3 cluster, const ReduceArgs
     attr[0].val.clusterDim.z = cluster.z;
     cfg.attrs = attr;
     cfg.numAttrs = (cluster.x * cluster.y * cluster.z > 1) ? 1 : 0;
+    if (cluster.x * cluster.y * cluster.z > 8) {  // 16-CTA clusters are "non-portable": opt in once per kernel
+        static bool opted = false;
+        if (!opted) {
+            KF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            opted = true;
+        }
+    }
     KF_CUDA(cudaLaunchKernelEx(&cfg, kernel, args));
     rt.post_launch(name);
 }
 
-static int pick_splits(int64_t base_ctas, int64_t R, int64_t min_rows_per_cta, int max_splits) {
-    const int64_t target = (int64_t)Runtime::get().props().sm_count * 4;
+constexpr int kMaxCounters = 8192;
+// zero-initialised, self-resetting arrival counters shared by every split reduction (stream-ordered reuse)
+static uint32_t *arrival_counters() {
+    static uint32_t *buf = nullptr;
+    if (!buf) {
+        Runtime &rt = Runtime::get();
+        KF_CUDA(cudaMalloc(&buf, kMaxCounters * sizeof(uint32_t)));
+        rt.memset_async(buf, 0, kMaxCounters * sizeof(uint32_t));
+    }
+    return buf;
+}
+
+static int pick_splits(int64_t base_ctas, int64_t R, int64_t min_rows_per_cta, int max_splits, int ctas_per_sm = 8) {
+    const int64_t target = (int64_t)Runtime::get().props().sm_count * ctas_per_sm;
     int S = 1;
     while (S < max_splits && base_ctas * S < target && R / (S * 2) >= min_rows_per_cta) S *= 2;
     return S;
 }
 
+template <typename Tin, typename Tout, typename A, int V>
+static void launch_rows_w(const ReduceArgs &a, int W, bool vec_ok) {
+    Runtime &rt = Runtime::get();
+    const int64_t rows_per_cta = 8 / W;
+    const int64_t g = (a.rows + rows_per_cta - 1) / rows_per_cta;
+    KF_CHECK(g < (int64_t)0x7FFFFFFF);
+    const unsigned grid = (unsigned)g;
+#define KF_ROWS(WW)                                                                                       \
+    do {                                                                                                  \
+        if (vec_ok) reduce_rows_kernel<Tin, Tout, A, V, WW><<<grid, 256, 0, rt.stream()>>>(a);            \
+        else reduce_rows_kernel<Tin, Tout, A, 1, WW><<<grid, 256, 0, rt.stream()>>>(a);                   \
+    } while (0)
+    switch (W) {
+    case 1: KF_ROWS(1); break;
+    case 2: KF_ROWS(2); break;
+    case 4: KF_ROWS(4); break;
+    default: KF_ROWS(8); break;
+    }
+#undef KF_ROWS
+    rt.post_launch("reduce_rows_kernel");
+}
+
 template <typename Tin, typename Tout, typename A>
-static void reduce_rows(const void *in, void *out, int64_t rows, int64_t R, const ReducePlan &pl, int64_t factor_i, bool final_stage_of_partials) {
+static void reduce_rows(const void *in, void *out, int64_t rows, int64_t R, const ReducePlan &pl, int64_t factor_i) {
     constexpr int V = 16 / sizeof(Tin);
     const bool vec_ok = ((uintptr_t)in % 16 == 0) && (R % V == 0);
     ReduceArgs a{};
     a.in = in; a.out = out; a.rows = rows; a.R = R; a.inner = 1;
     a.is_mean = pl.is_mean; a.factor_f = pl.factor; a.factor_i = factor_i;
-    a.S = 1; a.C = 1; a.chunk = R; a.write_partial = 0;
+    a.S = 1; a.C = 1; a.chunk = R;
     Runtime &rt = Runtime::get();
     const int64_t sms = rt.props().sm_count;
-    if (rows >= sms * 4 && R <= 16384) {  // plenty of rows: warp per row
-        KF_CHECK((rows + 7) / 8 < (int64_t)0x7FFFFFFF);
-        const unsigned grid = (unsigned)((rows + 7) / 8);
-        if (vec_ok) reduce_rows_warp_kernel<Tin, Tout, A, V><<<grid, 256, 0, rt.stream()>>>(a);
-        else reduce_rows_warp_kernel<Tin, Tout, A, 1><<<grid, 256, 0, rt.stream()>>>(a);
-        rt.post_launch("reduce_rows_warp_kernel");
+    // W warps per row: as many as keep >= 8 vector loads per lane, until the grid has >= 8 CTAs per SM
+    int W = 1;
+    while (W < 8 && (rows + (8 / W) - 1) / (8 / W) < sms * 8 && R / (W * 2) >= (int64_t)32 * V * 8) W *= 2;
+    const int64_t ctas = (rows + (8 / W) - 1) / (8 / W);
+    if (ctas >= sms * 2 || R < (int64_t)256 * V * 16) {  // enough rows (or rows too short to split): no cross-CTA step
+        launch_rows_w<Tin, Tout, A, V>(a, W, vec_ok);
         return;
     }
-    KF_CHECK(rows <= 65535 * 32768ll, "too many rows");
-    int S = final_stage_of_partials ? 1 : pick_splits(rows, R, 2048, 1024);
+    // few long rows: split R over S CTAs; clusters of up to 8 fold through DSMEM, the last cluster finishes
+    KF_CHECK(rows <= 65535, "row count too large for the split reduce");  // grid.y limit
+    int S = pick_splits(rows, R, (int64_t)256 * V * 4, 1024);
     int C = S < 8 ? S : 8;
+    if (const char *e = std::getenv("KF_RED_S")) S = std::atoi(e);
+    if (const char *e = std::getenv("KF_RED_C")) C = std::min(S, std::atoi(e));
     int64_t chunk = (R + S - 1) / S;
     chunk = (chunk + V * 256 - 1) / (V * 256) * (V * 256);  // keep chunks vector- and block-aligned
     a.S = S; a.C = C; a.chunk = chunk;
     const int nparts = S / C;
+    KF_CHECK(rows <= kMaxCounters);
     Scratch partial(nparts > 1 ? sizeof(A) * rows * nparts : 16);
-    if (nparts > 1) {
-        a.out = partial.p;
-        a.write_partial = 1;
-    }
-    KF_CHECK(rows <= 65535, "row count too large for the split reduce");  // grid.y limit
+    a.partial = partial.p;
+    a.counter = arrival_counters();
     dim3 grid((unsigned)S, (unsigned)rows, 1), cluster((unsigned)C, 1, 1);
-    if (vec_ok) launch_clustered(reduce_rows_block_kernel<Tin, Tout, A, V>, grid, cluster, a, "reduce_rows_block_kernel");
-    else launch_clustered(reduce_rows_block_kernel<Tin, Tout, A, 1>, grid, cluster, a, "reduce_rows_block_kernel");
-    if (nparts > 1) reduce_rows<A, Tout, A>(partial.p, out, rows, nparts, pl, factor_i, true);
+    if (vec_ok) launch_clustered(reduce_rows_split_kernel<Tin, Tout, A, V>, grid, cluster, a, "reduce_rows_split_kernel");
+    else launch_clustered(reduce_rows_split_kernel<Tin, Tout, A, 1>, grid, cluster, a, "reduce_rows_split_kernel");
 }
 
 template <typename Tin, typename Tout, typename A>
-static void reduce_cols(const void *in, void *out, int64_t outer, int64_t R, int64_t inner, const ReducePlan &pl, int64_t factor_i,
-                        bool final_stage_of_partials) {
+static void reduce_cols(const void *in, void *out, int64_t outer, int64_t R, int64_t inner, const ReducePlan &pl, int64_t factor_i) {
     constexpr int V = 16 / sizeof(Tin);
     const bool vec_ok = ((uintptr_t)in % 16 == 0) && (inner % V == 0);
     const int vec = vec_ok ? V : 1;
@@ -264,19 +428,22 @@ static void reduce_cols(const void *in, void *out, int64_t outer, int64_t R, int
     a.is_mean = pl.is_mean; a.factor_f = pl.factor; a.factor_i = factor_i;
     const int64_t tiles = (inner + 32 * vec - 1) / (32 * vec);
     KF_CHECK(outer <= 65535, "outer too large for the column reduce");
-    int S = final_stage_of_partials ? 1 : pick_splits(tiles * outer, R, 16, 256);
+    int S = pick_splits(tiles * outer, R, 128, 256, 4);
     int C = S < 8 ? S : 8;
-    a.S = S; a.C = C; a.chunk = (R + S - 1) / S; a.write_partial = 0;
-    const int nparts = S / C;
-    Scratch partial(nparts > 1 ? sizeof(A) * outer * nparts * inner : 16);
-    if (nparts > 1) {
-        a.out = partial.p;
-        a.write_partial = 1;
+    if (const char *e = std::getenv("KF_RED_S")) S = std::atoi(e);  // tuning hooks (tools/gpu_tune_reduce.py)
+    if (const char *e = std::getenv("KF_RED_C")) C = std::min(S, std::atoi(e));
+    int nparts = S / C;
+    if (nparts > 1 && tiles * outer > kMaxCounters) {  // cannot happen with the target above; stay safe
+        S = C;
+        nparts = 1;
     }
+    a.S = S; a.C = C; a.chunk = (R + S - 1) / S;
+    Scratch partial(nparts > 1 ? sizeof(A) * outer * tiles * nparts * 32 * vec : 16);
+    a.partial = partial.p;
+    a.counter = arrival_counters();
     dim3 grid((unsigned)tiles, (unsigned)S, (unsigned)outer), cluster(1, (unsigned)C, 1);
     if (vec_ok) launch_clustered(reduce_cols_kernel<Tin, Tout, A, V>, grid, cluster, a, "reduce_cols_kernel");
     else launch_clustered(reduce_cols_kernel<Tin, Tout, A, 1>, grid, cluster, a, "reduce_cols_kernel");
-    if (nparts > 1) reduce_cols<A, Tout, A>(partial.p, out, outer, nparts, inner, pl, factor_i, true);
 }
 
 template <typename T, typename A>
@@ -284,20 +451,11 @@ static void reduce_typed(const ReducePlan &p) {
     int64_t factor_i = 1;
     if (p.is_mean && std::is_same<A, int64_t>::value) factor_i = (int64_t)p.factor;  // caller pre-computed the integer factor
     if (p.inner == 1) {
-        // rows > 65535 with few-splits path is handled by the warp kernel threshold; very many long rows fall back to it too
-        if (p.outer > 65535 && !(p.outer >= Runtime::get().props().sm_count * 4 && p.R <= 16384)) {
-            // long rows AND many of them: process in slabs of 65535 rows
-            for (int64_t r0 = 0; r0 < p.outer; r0 += 65535) {
-                const int64_t nr = std::min<int64_t>(65535, p.outer - r0);
-                reduce_rows<T, T, A>((const T *)p.in + r0 * p.R, (T *)p.out + r0, nr, p.R, p, factor_i, false);
-            }
-        } else {
-            reduce_rows<T, T, A>(p.in, p.out, p.outer, p.R, p, factor_i, false);
-        }
+        reduce_rows<T, T, A>(p.in, p.out, p.outer, p.R, p, factor_i);
     } else {
         for (int64_t o0 = 0; o0 < p.outer; o0 += 65535) {
             const int64_t no = std::min<int64_t>(65535, p.outer - o0);
-            reduce_cols<T, T, A>((const T *)p.in + o0 * p.R * p.inner, (T *)p.out + o0 * p.inner, no, p.R, p.inner, p, factor_i, false);
+            reduce_cols<T, T, A>((const T *)p.in + o0 * p.R * p.inner, (T *)p.out + o0 * p.inner, no, p.R, p.inner, p, factor_i);
         }
     }
 }

@@ -457,16 +457,25 @@ topk_select_kernel(const U *__restrict__ in, U *__restrict__ values, int64_t *__
 // exact radix-select top-k straight from global memory (any n, k <= TK_CAP); used for overflowed rows
 template <typename U>
 __global__ void __launch_bounds__(TK_THREADS, 1)
-topk_exact_kernel(const U *__restrict__ in, U *__restrict__ values, int64_t *__restrict__ indices, const int n, const int k,
-                  const int kind, const bool largest, const int *__restrict__ only_rows) {
+topk_exact_kernel(const U *__restrict__ in, U *__restrict__ values, int64_t *__restrict__ indices, const int64_t nrows, const int n,
+                  const int k, const int kind, const bool largest, const int *__restrict__ only_rows) {
     __shared__ U ck[TK_CAP];
     __shared__ uint32_t ci[TK_CAP];
     __shared__ uint32_t hist[256];
     __shared__ uint32_t scan_w[32];
     __shared__ U s_prefix;
     __shared__ int s_need, s_count, s_eq_taken;
-    const int64_t row = blockIdx.x;
-    if (only_rows && !only_rows[row]) return;
+    // rows are strided over the (persistent) grid; flags are scanned 1024 rows at a time so that the common
+    // "nothing overflowed" case costs one global load and one barrier per CTA
+    for (int64_t batch = blockIdx.x; batch < nrows; batch += (int64_t)gridDim.x * TK_THREADS) {
+    if (only_rows) {
+        const int64_t r = batch + (int64_t)threadIdx.x * gridDim.x;
+        const int f = r < nrows ? only_rows[r] : 0;
+        if (!__syncthreads_or(f)) continue;
+    }
+    for (int64_t row = batch; row < nrows && row < batch + (int64_t)gridDim.x * TK_THREADS; row += gridDim.x) {
+    if (only_rows && !only_rows[row]) continue;  // block-uniform
+    __syncthreads();
     const U *src = in + row * n;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const bool desc_key = !largest;
@@ -536,7 +545,223 @@ topk_exact_kernel(const U *__restrict__ in, U *__restrict__ values, int64_t *__r
         }
         __syncthreads();
     }
+    __syncthreads();
     emit_topk<U>(ck, ci, s_count, k, values + row * k, indices + row * k, kind, desc_key);
+    }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// top-k, 32-bit keys, k <= 256: two-pass select that reads HBM exactly once.
+//   pass 1  streams the row (16-byte no-allocate loads, 8 in flight per thread) and keeps only the maximum of every
+//           8-key group in registers; no key stays on chip, so a 256-thread CTA needs ~50 registers per thread and
+//           several CTAs (rows) share an SM: while one row is being selected, the others keep HBM busy.
+//   select  T1 = exact k-th largest THREAD maximum (warp knock-outs give a loose bound T0, the thread maxima >= T0
+//           are rank-counted in shared memory).  At least k keys are >= T1, and only ~k + a few in expectation.
+//   pass 2  re-reads ONLY the 8-key groups whose maximum reaches T1 (L2 hits: the row was read microseconds ago),
+//           compacts the keys >= T1 and rank-sorts them on 64-bit composites (key << 32 | ~index): ties keep the
+//           lowest index, exactly as the reference's stable sort does.
+// ------------------------------------------------------------------------------------------------
+constexpr int TP_THREADS = 256;
+constexpr int TP_WARPS = TP_THREADS / 32;
+constexpr int TP_CAP = 1024;  // candidate capacity; overflowing rows (massive ties) go to the exact kernel
+
+// order-preserving key with the kind fixed at compile time (2 instructions per fp32 key); `flip` folds the complement in
+template <int KIND>
+__device__ __forceinline__ uint32_t key32(uint32_t x, uint32_t flip) {
+    if (KIND == KEY_FLOAT) return x ^ (((uint32_t)((int32_t)x >> 31)) | 0x80000000u) ^ flip;
+    if (KIND == KEY_SINT) return x ^ 0x80000000u ^ flip;
+    return x ^ flip;
+}
+template <int KIND>
+__device__ __forceinline__ uint32_t unkey32(uint32_t k, uint32_t flip) {
+    k ^= flip;
+    if (KIND == KEY_FLOAT) return (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
+    if (KIND == KEY_SINT) return k ^ 0x80000000u;
+    return k;
+}
+__device__ __forceinline__ uint4 ldg_stream16(const uint32_t *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+template <int NB, int KIND>  // NB batches of 8 x 16 bytes per thread: n <= NB * 8192
+__global__ void __launch_bounds__(TP_THREADS, 3)
+topk_twopass_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ values, int64_t *__restrict__ indices, const int n, const int k,
+                    const bool largest, int *__restrict__ overflow_rows) {
+    __shared__ __align__(16) unsigned long long cand[TP_CAP];
+    __shared__ __align__(16) uint32_t tmax_list[TP_THREADS];
+    __shared__ int rank_part[TP_THREADS];
+    __shared__ uint32_t warp_thr[TP_WARPS];
+    __shared__ uint32_t s_t1;
+    __shared__ int count, count_tm;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int64_t row = blockIdx.x;
+    const uint32_t *__restrict__ src = in + row * n;
+    const uint32_t flip = largest ? 0u : 0xffffffffu;  // smallest-k == largest-k of the complemented keys
+    if (tid == 0) {
+        count = 0;
+        count_tm = 0;
+    }
+    // ---- pass 1: group maxima (group g = loads 2g, 2g+1 of this thread = 8 keys)
+    uint32_t gmax[NB * 4];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int p = ((b * 8 + u) * TP_THREADS + tid) * 4;
+            v[u] = make_uint4(0, 0, 0, 0);
+            if (p < n) v[u] = ldg_stream16(src + p);  // n % 4 == 0 on this path
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int p = ((b * 8 + u) * TP_THREADS + tid) * 4;
+            uint32_t m4 = max(max(key32<KIND>(v[u].x, flip), key32<KIND>(v[u].y, flip)), max(key32<KIND>(v[u].z, flip), key32<KIND>(v[u].w, flip)));
+            if (p >= n) m4 = 0u;  // padding sits below every accepted threshold
+            if (u & 1) gmax[b * 4 + (u >> 1)] = max(gmax[b * 4 + (u >> 1)], m4);
+            else gmax[b * 4 + (u >> 1)] = m4;
+        }
+    }
+    uint32_t tmax = 0;
+#pragma unroll
+    for (int g = 0; g < NB * 4; ++g) tmax = max(tmax, gmax[g]);
+    // ---- loose lower bound T0 of the k-th largest thread maximum: every warp contributes its j-th largest lane value,
+    // so >= 8 j >= k thread maxima are >= the minimum over warps
+    {
+        const int j = (k + TP_WARPS - 1) / TP_WARPS;
+        uint32_t v = tmax;
+        for (int it = 1; it < j; ++it) {  // knock out the current warp maximum (one lane) j - 1 times
+            const uint32_t m = __reduce_max_sync(0xffffffffu, v);
+            const uint32_t holders = __ballot_sync(0xffffffffu, v == m);
+            if (lane == __ffs(holders) - 1) v = 0;
+        }
+        const uint32_t tw = __reduce_max_sync(0xffffffffu, v);
+        if (lane == 0) warp_thr[w] = tw;
+    }
+    __syncthreads();
+    const uint32_t t0 = __reduce_min_sync(0xffffffffu, warp_thr[lane & (TP_WARPS - 1)]);
+    // ---- list of the thread maxima >= T0 (at least k of them)
+    {
+        const bool hit = t0 != 0 && tmax >= t0;
+        const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+        if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&count_tm, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (hit) tmax_list[base + __popc(bal & ((1u << lane) - 1u))] = tmax;
+        }
+    }
+    __syncthreads();
+    const int m = count_tm;
+    // ---- T1 = exact k-th largest thread maximum.  Rank counting over all threads: entry e = tid % cp2 against slice
+    // g = tid / cp2 (warp-uniform) of the list; earlier list positions win ties, so ranks are a permutation.
+    if (t0 != 0) {
+        int cp2 = 32;
+        while (cp2 < m) cp2 <<= 1;
+        const int G = TP_THREADS / cp2;
+        const int e = tid & (cp2 - 1), g = tid / cp2;
+        const int per = (m + G - 1) / G;
+        const int lo = g * per, hi = min(m, lo + per);
+        int rank = 0;
+        uint32_t mine = 0;
+        if (e < m) {
+            mine = tmax_list[e];
+            const int mid = min(max(e, lo), hi);
+            const uint32_t ge_thr = mine - 1u;  // values are >= t0 >= 1: "a >= mine" is "a > mine - 1"
+#pragma unroll 4
+            for (int q = lo; q < mid; ++q) rank += tmax_list[q] > ge_thr ? 1 : 0;
+#pragma unroll 4
+            for (int q = mid; q < hi; ++q) rank += tmax_list[q] > mine ? 1 : 0;
+        }
+        rank_part[tid] = rank;
+        __syncthreads();
+        if (tid < m) {
+            int r = 0;
+            for (int gg = 0; gg < G; ++gg) r += rank_part[gg * cp2 + tid];
+            if (r == k - 1) s_t1 = mine;
+        }
+    } else {
+        if (tid == 0) s_t1 = 0u;
+    }
+    __syncthreads();
+    const uint32_t t1 = s_t1;
+    // ---- pass 2: re-read the groups that can hold a key >= T1, compact those keys.  Each lane walks ITS OWN hit groups
+    // (bitmask + runtime address), so the L2 round trips of all lanes of a warp overlap instead of serialising per group.
+    {
+        uint32_t hm = 0;
+        if (t1 != 0) {
+#pragma unroll
+            for (int g = 0; g < NB * 4; ++g) hm |= gmax[g] >= t1 ? (1u << g) : 0u;
+        }
+        while (__any_sync(0xffffffffu, hm != 0)) {
+            if (hm) {
+                const int g = __ffs(hm) - 1;
+                hm &= hm - 1;
+                const int p0 = (g * 2 * TP_THREADS + tid) * 4, p1 = p0 + TP_THREADS * 4;
+                uint4 v0 = make_uint4(0, 0, 0, 0), v1 = make_uint4(0, 0, 0, 0);
+                if (p0 < n) v0 = *reinterpret_cast<const uint4 *>(src + p0);
+                if (p1 < n) v1 = *reinterpret_cast<const uint4 *>(src + p1);
+                const uint32_t kk[8] = {key32<KIND>(v0.x, flip), key32<KIND>(v0.y, flip), key32<KIND>(v0.z, flip), key32<KIND>(v0.w, flip),
+                                        key32<KIND>(v1.x, flip), key32<KIND>(v1.y, flip), key32<KIND>(v1.z, flip), key32<KIND>(v1.w, flip)};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int p = (e < 4 ? p0 : p1) + (e & 3);
+                    if (kk[e] >= t1 && p < n) {
+                        const int slot = atomicAdd(&count, 1);
+                        if (slot < TP_CAP) cand[slot] = ((unsigned long long)kk[e] << 32) | (unsigned long long)(0xffffffffu - (uint32_t)p);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int c = t1 != 0 ? count : TP_CAP + 1;
+    if (c > TP_CAP) {  // massive ties (or an all-padding threshold): the exact kernel redoes this row
+        if (tid == 0) overflow_rows[row] = 1;
+        return;
+    }
+    // ---- order the candidates: composites are unique, rank < k is the sorted top-k
+    if (c <= TP_THREADS) {
+        int cp2 = 32;
+        while (cp2 < c) cp2 <<= 1;
+        const int G = TP_THREADS / cp2;
+        const int e = tid & (cp2 - 1), g = tid / cp2;
+        const int per = (((c + G - 1) / G) + 1) & ~1;  // even slice length keeps the 16-byte reads aligned
+        const int lo = g * per, hi = min(c, lo + per);
+        const unsigned long long mine = cand[min(e, c - 1)];
+        int rank = 0;
+        if (e < c) {
+            int q = lo;
+#pragma unroll 4
+            for (; q + 1 < hi; q += 2) {
+                const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(&cand[q]);
+                rank += (a.x > mine ? 1 : 0) + (a.y > mine ? 1 : 0);
+            }
+            if (q < hi) rank += cand[q] > mine ? 1 : 0;
+        }
+        rank_part[tid] = rank;
+        __syncthreads();
+        if (tid < c) {
+            int r = 0;
+            for (int gg = 0; gg < G; ++gg) r += rank_part[gg * cp2 + tid];
+            if (r < k) {
+                values[row * k + r] = unkey32<KIND>((uint32_t)(mine >> 32), flip);
+                indices[row * k + r] = (int64_t)(0xffffffffu - (uint32_t)mine);
+            }
+        }
+    } else {
+        for (int ci = tid; ci < c; ci += TP_THREADS) {  // 256 < c <= 1024: rare, plain loop
+            const unsigned long long mine = cand[ci];
+            int rank = 0;
+            for (int q = 0; q < c; ++q) rank += cand[q] > mine ? 1 : 0;
+            if (rank < k) {
+                values[row * k + rank] = unkey32<KIND>((uint32_t)(mine >> 32), flip);
+                indices[row * k + rank] = (int64_t)(0xffffffffu - (uint32_t)mine);
+            }
+        }
+    }
 }
 
 template <typename U>
@@ -545,11 +770,12 @@ static bool topk_typed(const void *in, void *values, int64_t *indices, int kind,
     cudaStream_t st = rt.stream();
     KF_CHECK(nseg < (int64_t)0x7FFFFFFF);
     const unsigned grid = (unsigned)nseg;
+    const unsigned pgrid = (unsigned)std::min<int64_t>(nseg, (int64_t)rt.props().sm_count * 2);  // persistent, rows strided
     const bool fast = k <= 1024 && n >= 2048 && n <= 32 * TK_THREADS;
     if (!fast) {
         // rows too long for registers: exact select when k fits the candidate buffer and rows are long enough to pay
         if (k <= 1024 && n > 32 * TK_THREADS) {
-            topk_exact_kernel<U><<<grid, TK_THREADS, 0, st>>>((const U *)in, (U *)values, indices, (int)n, (int)k, kind, largest, nullptr);
+            topk_exact_kernel<U><<<pgrid, TK_THREADS, 0, st>>>((const U *)in, (U *)values, indices, nseg, (int)n, (int)k, kind, largest, nullptr);
             rt.post_launch("topk_exact_kernel");
             return true;
         }
@@ -560,20 +786,38 @@ static bool topk_typed(const void *in, void *values, int64_t *indices, int kind,
     const bool vec = sizeof(U) == 4 && n % 4 == 0 && ((uintptr_t)in % 16 == 0);
     int items = 4;
     while ((int64_t)items * TK_THREADS < n) items *= 2;
-#define KF_TOPK_LAUNCH(IT)                                                                                                    \
-    do {                                                                                                                      \
-        if (vec) topk_select_kernel<U, IT, true><<<grid, TK_THREADS, 0, st>>>((const U *)in, (U *)values, indices, (int)n, (int)k, kind, largest, flags.as<int>()); \
-        else topk_select_kernel<U, IT, false><<<grid, TK_THREADS, 0, st>>>((const U *)in, (U *)values, indices, (int)n, (int)k, kind, largest, flags.as<int>()); \
+    if (vec && k <= TP_THREADS / 2) {  // beyond k = 128 the thread-maximum threshold gets loose (k = 256 would accept ~4 % of the row)
+        // 32-bit keys, 16-byte aligned rows: two-pass select, one 256-thread CTA per row, several rows per SM
+        const int nb = n <= 8192 ? 1 : (n <= 16384 ? 2 : 4);
+#define KF_TOPK_TP2(NBV, KD) \
+    topk_twopass_kernel<NBV, KD><<<grid, TP_THREADS, 0, st>>>((const uint32_t *)in, (uint32_t *)values, indices, (int)n, (int)k, largest, flags.as<int>())
+#define KF_TOPK_TP(NBV)                                      \
+    do {                                                     \
+        if (kind == KEY_FLOAT) KF_TOPK_TP2(NBV, KEY_FLOAT);  \
+        else if (kind == KEY_SINT) KF_TOPK_TP2(NBV, KEY_SINT); \
+        else KF_TOPK_TP2(NBV, KEY_UINT);                     \
     } while (0)
-    switch (items) {
-    case 4: KF_TOPK_LAUNCH(4); break;
-    case 8: KF_TOPK_LAUNCH(8); break;
-    case 16: KF_TOPK_LAUNCH(16); break;
-    default: KF_TOPK_LAUNCH(32); break;
-    }
+        switch (nb) {
+        case 1: KF_TOPK_TP(1); break;
+        case 2: KF_TOPK_TP(2); break;
+        default: KF_TOPK_TP(4); break;
+        }
+#undef KF_TOPK_TP
+#undef KF_TOPK_TP2
+        rt.post_launch("topk_twopass_kernel");
+    } else {
+#define KF_TOPK_LAUNCH(IT)                                                                                                    \
+    topk_select_kernel<U, IT, false><<<grid, TK_THREADS, 0, st>>>((const U *)in, (U *)values, indices, (int)n, (int)k, kind, largest, flags.as<int>())
+        switch (items) {
+        case 4: KF_TOPK_LAUNCH(4); break;
+        case 8: KF_TOPK_LAUNCH(8); break;
+        case 16: KF_TOPK_LAUNCH(16); break;
+        default: KF_TOPK_LAUNCH(32); break;
+        }
 #undef KF_TOPK_LAUNCH
-    rt.post_launch("topk_select_kernel");
-    topk_exact_kernel<U><<<grid, TK_THREADS, 0, st>>>((const U *)in, (U *)values, indices, (int)n, (int)k, kind, largest, flags.as<int>());
+        rt.post_launch("topk_select_kernel");
+    }
+    topk_exact_kernel<U><<<pgrid, TK_THREADS, 0, st>>>((const U *)in, (U *)values, indices, nseg, (int)n, (int)k, kind, largest, flags.as<int>());
     rt.post_launch("topk_exact_kernel");
     return true;
 }

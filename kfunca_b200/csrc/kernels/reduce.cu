@@ -213,11 +213,18 @@ __global__ void __launch_bounds__(256) reduce_rows_split_kernel(const ReduceArgs
 }
 
 // ------------------------------------------------------------------ columns
-template <typename Tin, typename Tout, typename A, int VEC>
+// LPR lanes run along `inner` (16-byte vectors), so a warp covers 32 / LPR rows per load instruction and a CTA tile is
+// LPR * VEC columns wide: narrow tiles give enough CTAs for the whole reduction to finish inside ONE 8-CTA cluster
+// (DSMEM fold, no global hand-shake) even when `inner` is only a few thousand columns.
+template <typename Tin, typename Tout, typename A, int VEC, int LPR>
 __global__ void __launch_bounds__(256) reduce_cols_kernel(const ReduceArgs a) {
-    __shared__ A part[8][32 * VEC];
+    constexpr int RPW = 32 / LPR;        // rows per warp-wide load
+    constexpr int PH = 8 * RPW;          // row phases per CTA
+    constexpr int WIDTH = LPR * VEC;     // columns per CTA
+    __shared__ A part[PH][WIDTH];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t col = ((int64_t)blockIdx.x * 32 + lane) * VEC;
+    const int cl = lane % LPR, ph = w * RPW + lane / LPR;
+    const int64_t col = ((int64_t)blockIdx.x * LPR + cl) * VEC;
     const int s = blockIdx.y;
     const int64_t o = blockIdx.z;
     const int64_t lo = (int64_t)s * a.chunk;
@@ -228,37 +235,37 @@ __global__ void __launch_bounds__(256) reduce_cols_kernel(const ReduceArgs a) {
     for (int j = 0; j < VEC; ++j) acc[j] = A(0);
     if (col < a.inner) {
         const Tin *__restrict__ p = reinterpret_cast<const Tin *>(a.in) + o * a.R * a.inner + col;
-        int64_t r = lo + w;
-        for (; r + 56 < hi; r += 64) {  // 8 independent 16-byte loads in flight per thread
+        int64_t r = lo + ph;
+        for (; r + 7 * PH < hi; r += 8 * PH) {  // 8 independent 16-byte loads in flight per thread
             Pack<Tin, VEC> pk[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) pk[u] = ld_stream<Tin, VEC>(reinterpret_cast<const Pack<Tin, VEC> *>(p + (r + 8 * u) * a.inner));
+            for (int u = 0; u < 8; ++u) pk[u] = ld_stream<Tin, VEC>(reinterpret_cast<const Pack<Tin, VEC> *>(p + (r + (int64_t)PH * u) * a.inner));
 #pragma unroll
             for (int u = 0; u < 8; ++u)
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) acc[j] += cvt_in<A>(pk[u].v[j]);
         }
-        for (; r < hi; r += 8) {
+        for (; r < hi; r += PH) {
             Pack<Tin, VEC> pk = ld_stream<Tin, VEC>(reinterpret_cast<const Pack<Tin, VEC> *>(p + r * a.inner));
 #pragma unroll
             for (int j = 0; j < VEC; ++j) acc[j] += cvt_in<A>(pk.v[j]);
         }
     }
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) part[w][lane * VEC + j] = acc[j];
+    for (int j = 0; j < VEC; ++j) part[ph][cl * VEC + j] = acc[j];
     __syncthreads();
-    // fold the 8 warps: thread t owns column slots t, t+256, ... (32*VEC slots)
-    for (int t = threadIdx.x; t < 32 * VEC; t += 256) {
+    // fold the row phases: thread t owns column slot t (WIDTH <= 256 slots)
+    for (int t = threadIdx.x; t < WIDTH; t += 256) {
         A v = A(0);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v += part[k][t];
+        for (int k = 0; k < PH; ++k) v += part[k][t];
         part[0][t] = v;
     }
     if (a.C > 1) {
         cg::cluster_group cluster = cg::this_cluster();
         cluster.sync();
         if (cluster.block_rank() == 0) {
-            for (int t = threadIdx.x; t < 32 * VEC; t += 256) {
+            for (int t = threadIdx.x; t < WIDTH; t += 256) {
                 A v0 = part[0][t], v1 = A(0), v2 = A(0), v3 = A(0);
                 int r = 1;
                 for (; r + 3 < a.C; r += 4) {  // independent DSMEM reads in flight
@@ -276,29 +283,28 @@ __global__ void __launch_bounds__(256) reduce_cols_kernel(const ReduceArgs a) {
     }
     __syncthreads();
     const int nparts = a.S / a.C;
-    const int width = 32 * VEC;
     if (nparts > 1) {
         const int64_t group = o * gridDim.x + blockIdx.x;
-        A *gp = reinterpret_cast<A *>(a.partial) + group * nparts * width;
-        if (!publish_and_elect<A>(a, gp, s / a.C, nparts, width, &part[0][0], a.counter + group)) return;
-        // parallel fold: 256 / width thread groups split the partials (fixed assignment => deterministic), 4 loads in flight
-        constexpr int GROUPS = (256 / (32 * VEC)) > 0 ? (256 / (32 * VEC)) : 1;
-        for (int t = threadIdx.x; t < width * GROUPS; t += 256) {
-            const int slot = t % width, g = t / width;
+        A *gp = reinterpret_cast<A *>(a.partial) + group * nparts * WIDTH;
+        if (!publish_and_elect<A>(a, gp, s / a.C, nparts, WIDTH, &part[0][0], a.counter + group)) return;
+        // parallel fold: 256 / WIDTH thread groups split the partials (fixed assignment => deterministic), 4 loads in flight
+        constexpr int GROUPS = (256 / WIDTH) > 0 ? (256 / WIDTH) : 1;
+        for (int t = threadIdx.x; t < WIDTH * GROUPS; t += 256) {
+            const int slot = t % WIDTH, g = t / WIDTH;
             A v0 = A(0), v1 = A(0), v2 = A(0), v3 = A(0);
             int k = g;
             for (; k + 3 * GROUPS < nparts; k += 4 * GROUPS) {
-                v0 += __ldcg(gp + (int64_t)k * width + slot);
-                v1 += __ldcg(gp + (int64_t)(k + GROUPS) * width + slot);
-                v2 += __ldcg(gp + (int64_t)(k + 2 * GROUPS) * width + slot);
-                v3 += __ldcg(gp + (int64_t)(k + 3 * GROUPS) * width + slot);
+                v0 += __ldcg(gp + (int64_t)k * WIDTH + slot);
+                v1 += __ldcg(gp + (int64_t)(k + GROUPS) * WIDTH + slot);
+                v2 += __ldcg(gp + (int64_t)(k + 2 * GROUPS) * WIDTH + slot);
+                v3 += __ldcg(gp + (int64_t)(k + 3 * GROUPS) * WIDTH + slot);
             }
-            for (; k < nparts; k += GROUPS) v0 += __ldcg(gp + (int64_t)k * width + slot);
+            for (; k < nparts; k += GROUPS) v0 += __ldcg(gp + (int64_t)k * WIDTH + slot);
             part[g][slot] = (v0 + v1) + (v2 + v3);
         }
         __syncthreads();
         if (GROUPS > 1) {
-            for (int t = threadIdx.x; t < width; t += 256) {
+            for (int t = threadIdx.x; t < WIDTH; t += 256) {
                 A v = part[0][t];
 #pragma unroll
                 for (int g = 1; g < GROUPS; ++g) v += part[g][t];
@@ -307,8 +313,8 @@ __global__ void __launch_bounds__(256) reduce_cols_kernel(const ReduceArgs a) {
             __syncthreads();
         }
     }
-    for (int t = threadIdx.x; t < width; t += 256) {
-        const int64_t c = (int64_t)blockIdx.x * width + t;
+    for (int t = threadIdx.x; t < WIDTH; t += 256) {
+        const int64_t c = (int64_t)blockIdx.x * WIDTH + t;
         if (c < a.inner) reinterpret_cast<Tout *>(a.out)[o * a.inner + c] = cvt_out<Tout, A>(finalize(part[0][t], a));
     }
 }
@@ -426,9 +432,18 @@ static void reduce_cols(const void *in, void *out, int64_t outer, int64_t R, int
     ReduceArgs a{};
     a.in = in; a.out = out; a.rows = outer; a.R = R; a.inner = inner;
     a.is_mean = pl.is_mean; a.factor_f = pl.factor; a.factor_i = factor_i;
-    const int64_t tiles = (inner + 32 * vec - 1) / (32 * vec);
     KF_CHECK(outer <= 65535, "outer too large for the column reduce");
-    int S = pick_splits(tiles * outer, R, 128, 256, 4);
+    const int64_t sms = Runtime::get().props().sm_count;
+    // lanes per row: narrow the CTA tile (32 -> 16 -> 8 lanes, never below one 128-byte line per row for 16-byte vectors)
+    // while an 8-way split — the most one cluster can fold without a global hand-shake — would leave SMs idle
+    int lpr = 32;
+    auto tiles_for = [&](int l) { return (inner + (int64_t)l * vec - 1) / ((int64_t)l * vec); };
+    // (measured at 4096 x 4096 fp32: ~3.5 CTAs per SM with 128 KB each beats 7 per SM with 64 KB: 14.4 us vs 18.3 us)
+    while (lpr > 8 && tiles_for(lpr) * outer * 8 < sms * 3 && R >= 512) lpr /= 2;
+    if (const char *e = std::getenv("KF_RED_LPR")) lpr = std::atoi(e);
+    const int64_t tiles = tiles_for(lpr);
+    const int ph = 8 * (32 / lpr);
+    int S = pick_splits(tiles * outer, R, (int64_t)ph * 4, 256, 3);
     int C = S < 8 ? S : 8;
     if (const char *e = std::getenv("KF_RED_S")) S = std::atoi(e);  // tuning hooks (tools/gpu_tune_reduce.py)
     if (const char *e = std::getenv("KF_RED_C")) C = std::min(S, std::atoi(e));
@@ -438,12 +453,21 @@ static void reduce_cols(const void *in, void *out, int64_t outer, int64_t R, int
         nparts = 1;
     }
     a.S = S; a.C = C; a.chunk = (R + S - 1) / S;
-    Scratch partial(nparts > 1 ? sizeof(A) * outer * tiles * nparts * 32 * vec : 16);
+    Scratch partial(nparts > 1 ? sizeof(A) * outer * tiles * nparts * lpr * vec : 16);
     a.partial = partial.p;
     a.counter = arrival_counters();
     dim3 grid((unsigned)tiles, (unsigned)S, (unsigned)outer), cluster(1, (unsigned)C, 1);
-    if (vec_ok) launch_clustered(reduce_cols_kernel<Tin, Tout, A, V>, grid, cluster, a, "reduce_cols_kernel");
-    else launch_clustered(reduce_cols_kernel<Tin, Tout, A, 1>, grid, cluster, a, "reduce_cols_kernel");
+#define KF_COLS(L)                                                                                                        \
+    do {                                                                                                                  \
+        if (vec_ok) launch_clustered(reduce_cols_kernel<Tin, Tout, A, V, L>, grid, cluster, a, "reduce_cols_kernel");     \
+        else launch_clustered(reduce_cols_kernel<Tin, Tout, A, 1, L>, grid, cluster, a, "reduce_cols_kernel");            \
+    } while (0)
+    switch (lpr) {
+    case 8: KF_COLS(8); break;
+    case 16: KF_COLS(16); break;
+    default: KF_COLS(32); break;
+    }
+#undef KF_COLS
 }
 
 template <typename T, typename A>

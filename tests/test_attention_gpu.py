@@ -106,10 +106,13 @@ def test_attention_backward_fp32(shape, dtype):
     np.testing.assert_allclose(gv.grad().numpy(), dv, rtol=tol, atol=tol)
 
 
-@pytest.mark.parametrize("shape", [(1, 2, 128, 128, 128), (2, 2, 256, 256, 64), (1, 2, 200, 200, 128)])
-def test_attention_backward_bf16(shape):
-    q, k, v = (to16(t, "bf16") for t in qkv(*shape))
-    do = to16(RNG.uniform(-1, 1, q.shape), "bf16")
+@pytest.mark.parametrize("dt", ["bf16", "fp16"])
+@pytest.mark.parametrize("shape", [(1, 2, 128, 128, 128), (2, 2, 256, 256, 64), (1, 2, 200, 200, 128), (1, 2, 300, 200, 64), (1, 1, 100, 333, 128),
+                                   (1, 2, 1024, 1024, 128), (2, 1, 640, 640, 64), (1, 1, 1, 1, 64), (1, 1, 65, 129, 128)])
+def test_attention_backward_16bit(dt, shape):
+    """tcgen05 backward (attention_bwd_tc.cu): dQ, dK, dV against the float64 oracle of the same 16-bit inputs"""
+    q, k, v = (to16(t, dt) for t in qkv(*shape))
+    do = to16(RNG.uniform(-1, 1, q.shape), dt)
     out, lse = kf.causal_attention_fwd(g(q), g(k), g(v))
     dq, dk, dv = kf.causal_attention_bwd(g(do), g(q), g(k), g(v), out, lse)
     eq, ek, ev = O.causal_attention_bwd(q, k, v, do)
@@ -117,3 +120,12 @@ def test_attention_backward_bf16(shape):
         gotf = got.float().numpy().astype(np.float64)
         scale = np.abs(exp).max()
         assert np.all(np.abs(gotf - exp) <= 2e-2 * np.abs(exp) + 1e-2 * scale), float(np.abs(gotf - exp).max() / scale)
+
+
+def test_attention_backward_16bit_is_deterministic():
+    q, k, v = (to16(t, "bf16") for t in qkv(1, 2, 512, 512, 128))
+    do = to16(RNG.uniform(-1, 1, q.shape), "bf16")
+    out, lse = kf.causal_attention_fwd(g(q), g(k), g(v))
+    a = [t.float().numpy() for t in kf.causal_attention_bwd(g(do), g(q), g(k), g(v), out, lse)]
+    b = [t.float().numpy() for t in kf.causal_attention_bwd(g(do), g(q), g(k), g(v), out, lse)]
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))

@@ -53,7 +53,11 @@ if fams & {"attn", "attn_bwd"}:
     q.fill_(0.05)
     k.fill_(0.03)
     v.fill_(0.5)
+    do = kf.empty([Bq, H, S, D], kf.bfloat16, 0)
+    do.fill_(0.1)
     for _ in range(REPS):
-        o = kf.causal_attention(q, k, v)
+        o, lse = kf.causal_attention_fwd(q, k, v)
+        if "attn_bwd" in fams:
+            kf.causal_attention_bwd(do, q, k, v, o, lse)
 kf.synchronize()
 print("prof_ops done")

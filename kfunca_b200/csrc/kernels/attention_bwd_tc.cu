@@ -46,28 +46,90 @@ __device__ __forceinline__ uint32_t pack16b(float a, float b, int is_bf16) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&h);
 }
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack16t(float2 v) {
+    if (BF16) {
+        __nv_bfloat162 h = __float22bfloat162_rn(v);
+        return *reinterpret_cast<uint32_t *>(&h);
+    }
+    __half2 h = __float22half2_rn(v);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
 __device__ __forceinline__ float ex2_approx_b(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+
+// Element-wise phase of one streamed 64-column tile for one thread (= one stationary row):
+//   P = exp2(S c - lse2),  dS = P o (dP - delta)   ->  16-bit P over T0 (MODE_DKV only) and dS over T1, in tensor memory.
+// Instruction diet: packed fp32x2 FFMA / FADD / FMUL, one LDS.128 per column pair for the per-column (-lse2, -delta)
+// (MODE_DKV; per-row registers in MODE_DQ), the causal / ragged mask only in the MASKED instantiation (diagonal tiles),
+// and 16-column chunks double-buffered so the next tcgen05.ld is in flight while the current chunk is computed.
+// vb: [32 column pairs][-lse2(2c), -lse2(2c+1), -delta(2c), -delta(2c+1)]
+template <int MODE, bool MASKED, bool BF16>
+__device__ __forceinline__ void bwd_ew_tile(const uint32_t t_addr, const uint32_t vb_smem, const float2 nl_row, const float2 nd_row,
+                                            const float sc, const int lo, const int hi) {
+    const float2 sc2 = make_float2(sc, sc);
+    uint32_t s_r[2][16], dp_r[2][16];
+    tmem_ld16(t_addr, s_r[0]);
+    tmem_ld16(t_addr + 64, dp_r[0]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {  // 16 streamed columns per chunk
+        const int cur = c & 1;
+        if (c < 3) {
+            tmem_ld16(t_addr + (uint32_t)((c + 1) * 16), s_r[cur ^ 1]);
+            tmem_ld16(t_addr + 64 + (uint32_t)((c + 1) * 16), dp_r[cur ^ 1]);
+        }
+        uint32_t pk[8], dk[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+            float2 nl, nd;
+            if (MODE == MODE_DKV) {
+                float4 v;  // explicit ld.shared: the generic pointer would compile to LD.E
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(vb_smem + 8u * (c * 16 + i)));
+                nl = make_float2(v.x, v.y);
+                nd = make_float2(v.z, v.w);
+            } else {
+                nl = nl_row;
+                nd = nd_row;
+            }
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(s_r[cur][i]), __uint_as_float(s_r[cur][i + 1])), sc2, nl);
+            float2 pr = make_float2(ex2_approx_b(x.x), ex2_approx_b(x.y));
+            if (MASKED) {
+                const int col = c * 16 + i;
+                if (col < lo || col >= hi) pr.x = 0.f;
+                if (col + 1 < lo || col + 1 >= hi) pr.y = 0.f;
+            }
+            const float2 ds = __fmul2_rn(pr, __fadd2_rn(make_float2(__uint_as_float(dp_r[cur][i]), __uint_as_float(dp_r[cur][i + 1])), nd));
+            if (MODE == MODE_DKV) pk[i >> 1] = pack16t<BF16>(pr);
+            dk[i >> 1] = pack16t<BF16>(ds);
+        }
+        if (MODE == MODE_DKV) tmem_st8(t_addr + (uint32_t)(c * 8), pk);  // P^T over T0 (columns already consumed)
+        tmem_st8(t_addr + 64 + (uint32_t)(c * 8), dk);                     // dS over T1
+        if (c < 3) tmem_ld_wait();
+    }
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-// rowsum(dO o O) and the exp2-domain LSE: one warp per query row
+// rowsum(dO o O) and the exp2-domain LSE.  16-byte loads: D/8 lanes per query row, 256/(D/8) rows per CTA (D = 64 / 128).
 template <typename T>
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const T *__restrict__ o, const T *__restrict__ dout, const float *__restrict__ lse,
                                                             float *__restrict__ delta, float *__restrict__ lse2, const int64_t rows, const int D) {
-    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
-    const T *po = o + row * D, *pd = dout + row * D;
+    const int lpr = D >> 3;  // lanes per row: 8 or 16
+    const int64_t row = (int64_t)blockIdx.x * (256 / lpr) + threadIdx.x / lpr;
+    const int sub = threadIdx.x % lpr;
     float acc = 0.f;
-    for (int i = lane * 2; i < D; i += 64) {
-        acc += cvt_in<float>(po[i]) * cvt_in<float>(pd[i]) + cvt_in<float>(po[i + 1]) * cvt_in<float>(pd[i + 1]);
-    }
+    if (row < rows) {
+        const uint4 vo = __ldg(reinterpret_cast<const uint4 *>(o + row * D) + sub);
+        const uint4 vd = __ldg(reinterpret_cast<const uint4 *>(dout + row * D) + sub);
+        const T *po = reinterpret_cast<const T *>(&vo), *pd = reinterpret_cast<const T *>(&vd);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) {
+        for (int i = 0; i < 8; ++i) acc = fmaf(cvt_in<float>(po[i]), cvt_in<float>(pd[i]), acc);
+    }
+    for (int off = lpr >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (row < rows && sub == 0) {
         delta[row] = acc;
         lse2[row] = lse[row] * 1.4426950408889634f;
     }
@@ -234,25 +296,28 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_con
             my_lse = lse2[row_g];
             my_delta = delta[row_g];
         }
-        float *vec = svec + set * 256;  // [2 bufs][128]
+        float *vec = svec + set * 256;  // [2 bufs][32 column pairs][-lse2 x2, -delta x2]
         const int tsel = threadIdx.x & 127;  // thread index inside the set
-        float vnext = 0.f;                   // MODE_DKV: this thread's share of the next tile's lse2 / delta vector
-        auto load_vec = [&](int n) {         // n: tile ordinal; threads 0-63 fetch lse2, 64-127 fetch delta
+        // MODE_DKV: threads 0-63 fetch -lse2 of streamed row tsel, 64-127 fetch -delta; slot inside the pair-interleaved vector
+        const int vslot = 4 * ((tsel & 63) >> 1) + (tsel & 1) + (tsel < 64 ? 0 : 2);
+        float vnext = 0.f;
+        auto load_vec = [&](int n) {  // n: tile ordinal
             float v = 0.f;
             if (MODE == MODE_DKV && n < ntile) {
                 const int64_t qg = (int64_t)(t_lo + n) * 64 + (tsel & 63);
-                if (qg < p.Sq) v = (tsel < 64 ? lse2 : delta)[qg];
+                if (qg < p.Sq) v = -(tsel < 64 ? lse2 : delta)[qg];
             }
             return v;
         };
         vnext = load_vec(set);
+        const float2 nl_row = make_float2(-my_lse, -my_lse), nd_row = make_float2(-my_delta, -my_delta);
         for (int n = set; n < ntile; n += 2) {
             const int t = t_lo + n;
             const int64_t y0_row = (int64_t)t * 64;
             const int it = n >> 1;
             float *vb = vec + (it & 1) * 128;
             if (MODE == MODE_DKV) {
-                vb[tsel] = vnext;
+                vb[vslot] = vnext;
                 named_bar_sync(1 + set, 128);
                 vnext = load_vec(n + 2);
             }
@@ -267,37 +332,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_con
             const bool need_mask = __any_sync(0xffffffffu, lo > 0 || hi < 64);
             mbar_wait(&t_full[set], (uint32_t)(it & 1));
             tc_fence_after();
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {  // 32 streamed columns at a time
-                uint32_t s_r[32], dp_r[32];
-                tmem_ld32(t_addr + (uint32_t)(half * 32), s_r);
-                tmem_ld32(t_addr + 64 + (uint32_t)(half * 32), dp_r);
-                tmem_ld_wait();
-                uint32_t pk[16], dk[16];
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float l0, l1, d0, d1;
-                    if (MODE == MODE_DKV) {
-                        const float2 lv = *reinterpret_cast<const float2 *>(vb + half * 32 + i);
-                        const float2 dv = *reinterpret_cast<const float2 *>(vb + 64 + half * 32 + i);
-                        l0 = lv.x; l1 = lv.y; d0 = dv.x; d1 = dv.y;
-                    } else {
-                        l0 = l1 = my_lse;
-                        d0 = d1 = my_delta;
-                    }
-                    float p0 = ex2_approx_b(fmaf(__uint_as_float(s_r[i]), sc, -l0));
-                    float p1 = ex2_approx_b(fmaf(__uint_as_float(s_r[i + 1]), sc, -l1));
-                    if (need_mask) {
-                        const int c = half * 32 + i;
-                        if (c < lo || c >= hi) p0 = 0.f;
-                        if (c + 1 < lo || c + 1 >= hi) p1 = 0.f;
-                    }
-                    const float ds0 = p0 * (__uint_as_float(dp_r[i]) - d0), ds1 = p1 * (__uint_as_float(dp_r[i + 1]) - d1);
-                    pk[i >> 1] = pack16b(p0, p1, p.is_bf16);
-                    dk[i >> 1] = pack16b(ds0, ds1, p.is_bf16);
-                }
-                if (MODE == MODE_DKV) tmem_st16(t_addr + (uint32_t)(half * 16), pk);  // P^T over T0
-                tmem_st16(t_addr + 64 + (uint32_t)(half * 16), dk);                     // dS over T1
+            const uint32_t vbs = smem_u32(vb);
+            if (p.is_bf16) {
+                if (need_mask) bwd_ew_tile<MODE, true, true>(t_addr, vbs, nl_row, nd_row, sc, lo, hi);
+                else bwd_ew_tile<MODE, false, true>(t_addr, vbs, nl_row, nd_row, sc, lo, hi);
+            } else {
+                if (need_mask) bwd_ew_tile<MODE, true, false>(t_addr, vbs, nl_row, nd_row, sc, lo, hi);
+                else bwd_ew_tile<MODE, false, false>(t_addr, vbs, nl_row, nd_row, sc, lo, hi);
             }
             tmem_st_wait();
             tc_fence_before();
@@ -397,8 +438,9 @@ bool launch_attention_bwd_tc(const AttnBwdPlan &a) {
     Runtime &rt = Runtime::get();
     const int64_t rows = a.BH * a.Sq;
     Scratch delta((size_t)rows * 4), lse2((size_t)rows * 4);
-    KF_CHECK((rows + 7) / 8 < (int64_t)0x7FFFFFFF);
-    const unsigned pgrid = (unsigned)((rows + 7) / 8);
+    const int64_t rows_per_cta = 256 / (a.D / 8);
+    KF_CHECK((rows + rows_per_cta - 1) / rows_per_cta < (int64_t)0x7FFFFFFF);
+    const unsigned pgrid = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
     if (a.dtype == KF_BFLOAT16)
         attn_bwd_prep_kernel<__nv_bfloat16><<<pgrid, 256, 0, rt.stream()>>>((const __nv_bfloat16 *)a.out, (const __nv_bfloat16 *)a.dout, (const float *)a.lse,
                                                                             delta.as<float>(), lse2.as<float>(), rows, (int)a.D);

@@ -23,7 +23,10 @@ namespace kf {
 using namespace tc;
 
 constexpr int FA_BQ = 128, FA_BKV = 128;
-constexpr int FA_THREADS = 320;  // warps 0-3 softmax(tile 0), 4-7 softmax(tile 1), 8 MMA issuer, 9 TMA producer
+// warps 0-3 softmax(tile 0), 4-7 softmax(tile 1), 8 MMA issuer, 9 TMA producer, 10-11 idle.  12 warps = 3 whole warpgroups so that
+// setmaxnreg can move registers from the control warpgroup (40 / thread) to the two softmax warpgroups (232 / thread): a
+// softmax thread holds a whole 128-column S row plus the packed P chunk, which does not fit the 168 the launch gives everyone.
+constexpr int FA_THREADS = 384;
 constexpr int FA_NSTAGE = 4;     // K/V ring slots (K_0, V_0, K_1, V_1, ... in consumption order)
 
 struct AttnTcParams {
@@ -61,10 +64,106 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack16t(float2 v) {
+    if (BF16) {
+        __nv_bfloat162 h = __float22bfloat162_rn(v);
+        return *reinterpret_cast<uint32_t *>(&h);
+    }
+    __half2 h = __float22half2_rn(v);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+// 2^x for a pair on the FMA pipe (the MUFU unit does 16 ex2 / clk / SM, exactly as many cycles per 128x128 tile as the two
+// tile MMAs take, so a share of the exponentials is moved off it): round-to-nearest split x = j + f via the 1.5*2^23 magic
+// add, degree-3 minimax of 2^f on [-1/2, 1/2] (max rel. error 7.5e-5, far below the 16-bit P rounding), then j is added
+// into the exponent field.  x is clamped at -126 so the exponent arithmetic cannot wrap.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+    x.x = fmaxf(x.x, -126.f);
+    x.y = fmaxf(x.y, -126.f);
+    const float2 magic = make_float2(12582912.f, 12582912.f);
+    const float2 t = __fadd2_rn(x, magic);
+    const float2 r = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+    const float2 f = __ffma2_rn(r, make_float2(-1.f, -1.f), x);
+    float2 q = __ffma2_rn(f, make_float2(0.0551716648042202f, 0.0551716648042202f), make_float2(0.2426111251115799f, 0.2426111251115799f));
+    q = __ffma2_rn(q, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+    q = __ffma2_rn(q, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
+    return make_float2(__uint_as_float(__float_as_uint(q.x) + (__float_as_uint(t.x) << 23)),
+                       __uint_as_float(__float_as_uint(q.y) + (__float_as_uint(t.y) << 23)));
+}
+
+
+// Softmax of one 128-key block for one thread (= one query row): S row from tensor memory, [mask], row max, lazy
+// rescale of O / l, P = exp2(S c - m) written back over S as 16-bit, running row sum.  `lim`: columns > lim are masked.
+// POLY: of every 8 column pairs, this many take the FMA-pipe exp2
+template <int D, bool BF16, bool MASKED, int POLY>
+__device__ __forceinline__ void fwd_softmax_block(const uint32_t s_addr, const uint32_t o_addr, const float sc, const int lim, const bool first,
+                                                  float &m_ref, float &l_run) {
+    uint32_t s[4][32];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tmem_ld32(s_addr + (uint32_t)(c * 32), s[c]);
+    tmem_ld_wait();
+    if (MASKED) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (c * 32 + i > lim) s[c][i] = 0xff800000u;  // -inf
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+            mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
+            mx1 = fmaxf(mx1, fmaxf(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])));
+            mx2 = fmaxf(mx2, fmaxf(__uint_as_float(s[c][i + 4]), __uint_as_float(s[c][i + 5])));
+            mx3 = fmaxf(mx3, fmaxf(__uint_as_float(s[c][i + 6]), __uint_as_float(s[c][i + 7])));
+        }
+    const float m_new = fmaxf(m_ref, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc);
+    // lazy reference max: only move it (and rescale O, l) when the row max grew by more than 2^8
+    const bool grow = first ? true : (m_new - m_ref > 8.f);
+    if (!first && __any_sync(0xffffffffu, grow)) {
+        const float f = grow ? ((m_ref == -INFINITY) ? 0.f : ex2_approx(m_ref - m_new)) : 1.f;
+        l_run *= f;
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+            uint32_t orr[32];
+            tmem_ld32(o_addr + (uint32_t)(c * 32), orr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * f);
+            tmem_st32(o_addr + (uint32_t)(c * 32), orr);
+        }
+    }
+    if (grow) m_ref = m_new;
+    const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+    const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(-m_use, -m_use);
+    float2 rs2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 4; c += 2) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+                float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c + h][i]), __uint_as_float(s[c + h][i + 1])), sc2, nm2);
+                if (((i >> 1) & 7) < POLY) {
+                    x = ex2_poly2(x);
+                } else {
+                    x.x = ex2_approx(x.x);
+                    x.y = ex2_approx(x.y);
+                }
+                rs2 = __fadd2_rn(rs2, x);
+                pk[h * 16 + (i >> 1)] = pack16t<BF16>(x);
+            }
+        tmem_st32(s_addr + (uint32_t)(c * 16), pk);
+    }
+    l_run += rs2.x + rs2.y;
+}
 
 // One CTA = two 128-row query tiles (a 256-row "pair") of one (batch, head); the two tiles ping-pong on the
 // tensor pipe: while softmax warps work on S of tile t, the MMA warp runs P V + the next Q K^T of tile 1-t.
-template <int D>
+template <int D, int POLY>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                    const __grid_constant__ CUtensorMap tmap_v, const AttnTcParams p) {
@@ -89,14 +188,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const int bh = blockIdx.x / p.npairs;
     const int pr = p.npairs - 1 - (blockIdx.x % p.npairs);  // heaviest (longest KV range) pairs first
     const int q0 = pr * 2 * FA_BQ;
-    int nblk[2];
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
+    auto blocks_of = [&](int t) {
         const int64_t q0t = (int64_t)q0 + t * FA_BQ;
         const int64_t kv_end = min((int64_t)p.Skv, q0t + FA_BQ);
-        nblk[t] = q0t < p.Sq ? (int)((kv_end + FA_BKV - 1) / FA_BKV) : 0;
-    }
-    const int nmax = max(nblk[0], nblk[1]);
+        return q0t < p.Sq ? (int)((kv_end + FA_BKV - 1) / FA_BKV) : 0;
+    };
+    const int nblk0 = blocks_of(0), nblk1 = blocks_of(1);  // scalars: a dynamically indexed local array would live in local memory
+    const int nmax = max(nblk0, nblk1);
 
     if (warp == 9 && lane == 0) {
         prefetch_tmap(&tmap_q);
@@ -119,10 +217,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 9) {
+    if (warp >= 8) {
+      // control warpgroup (warps 10-11 idle): the register hand-over must sit INSIDE the role branch, ptxas budgets the
+      // code that follows a setmaxnreg by the value it names
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+      if (warp == 9) {
         // ===================================================== TMA producer
         if (lane == 0) {
-            const int ntile_q = nblk[1] > 0 ? 2 : 1;
+            const int ntile_q = nblk1 > 0 ? 2 : 1;
             mbar_arrive_expect_tx(q_full, ntile_q * TILE_BYTES);
             for (int t = 0; t < ntile_q; ++t)
 #pragma unroll
@@ -143,7 +245,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             }
         }
         __syncwarp();
-    } else if (warp == 8) {
+      } else if (warp == 8) {
         // ===================================================== MMA issuer
         if (lane == 0) {
             const int fmt = p.is_bf16 ? 1 : 0;
@@ -182,8 +284,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             {
                 const int sk = next_slot();  // K_0
                 tc_fence_after();
+#pragma unroll
                 for (int t = 0; t < 2; ++t)
-                    if (nblk[t] > 0) {
+                    if ((t ? nblk1 : nblk0) > 0) {
                         issue_s(t, kv_addr + sk * TILE_BYTES);
                         umma_commit(&s_full[t]);
                     }
@@ -193,12 +296,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                 const int sv = next_slot();  // V_{j-1}
                 const bool has_k = j < nmax;
                 const int sk = has_k ? next_slot() : 0;  // K_j
+#pragma unroll
                 for (int t = 0; t < 2; ++t) {
-                    if (j - 1 < nblk[t]) {
+                    const int nb_t = t ? nblk1 : nblk0;
+                    if (j - 1 < nb_t) {
                         mbar_wait(&p_full[t], (uint32_t)((j - 1) & 1));
                         tc_fence_after();
                         issue_pv(t, kv_addr + sv * TILE_BYTES, j > 1);
-                        if (j < nblk[t]) issue_s(t, kv_addr + sk * TILE_BYTES);
+                        if (j < nb_t) issue_s(t, kv_addr + sk * TILE_BYTES);
                         umma_commit(&s_full[t]);
                     }
                 }
@@ -207,10 +312,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             }
         }
         __syncwarp();
+      }
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
         // ===================================================== softmax + epilogue: thread = one query row of tile t
         const int t = warp >> 2, q = warp & 3;
-        const int n_t = nblk[t];
+        const int n_t = t ? nblk1 : nblk0;
         if (n_t > 0) {
             const int r = q * 32 + lane;
             const int64_t q0t = (int64_t)q0 + t * FA_BQ;
@@ -224,65 +331,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                 const int kv0 = j * FA_BKV;
                 mbar_wait(&s_full[t], (uint32_t)(j & 1));
                 tc_fence_after();
-                uint32_t s[4][32];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) tmem_ld32(s_addr + (uint32_t)(c * 32), s[c]);
-                tmem_ld_wait();
-                if ((kv0 + FA_BKV - 1 > q0t) || (kv0 + FA_BKV > p.Skv)) {  // diagonal / ragged block: mask in registers
-                    const int64_t lim64 = min(m_row, p.Skv - 1) - kv0;     // columns i > lim are masked
-                    const int lim = (int)max((int64_t)-1, min(lim64, (int64_t)127));
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (c * 32 + i > lim) s[c][i] = 0xff800000u;  // -inf
+                const bool masked = (kv0 + FA_BKV - 1 > q0t) || (kv0 + FA_BKV > p.Skv);  // diagonal / ragged block (CTA-uniform per tile)
+                const int64_t lim64 = min(m_row, p.Skv - 1) - kv0;                      // columns i > lim are masked
+                const int lim = (int)max((int64_t)-1, min(lim64, (int64_t)127));
+                if (p.is_bf16) {
+                    if (masked) fwd_softmax_block<D, true, true, POLY>(s_addr, o_addr, sc, lim, j == 0, m_ref, l_run);
+                    else fwd_softmax_block<D, true, false, POLY>(s_addr, o_addr, sc, lim, j == 0, m_ref, l_run);
+                } else {
+                    if (masked) fwd_softmax_block<D, false, true, POLY>(s_addr, o_addr, sc, lim, j == 0, m_ref, l_run);
+                    else fwd_softmax_block<D, false, false, POLY>(s_addr, o_addr, sc, lim, j == 0, m_ref, l_run);
                 }
-                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        mx0 = fmaxf(mx0, __uint_as_float(s[c][i]));
-                        mx1 = fmaxf(mx1, __uint_as_float(s[c][i + 1]));
-                        mx2 = fmaxf(mx2, __uint_as_float(s[c][i + 2]));
-                        mx3 = fmaxf(mx3, __uint_as_float(s[c][i + 3]));
-                    }
-                const float m_new = fmaxf(m_ref, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc);
-                // lazy reference max: only move it (and rescale O, l) when the row max grew by more than 2^8
-                const bool grow = j == 0 ? true : (m_new - m_ref > 8.f);
-                if (j > 0 && __any_sync(0xffffffffu, grow)) {
-                    const float f = grow ? ((m_ref == -INFINITY) ? 0.f : ex2_approx(m_ref - m_new)) : 1.f;
-                    l_run *= f;
-#pragma unroll 1
-                    for (int c = 0; c < D / 32; ++c) {
-                        uint32_t orr[32];
-                        tmem_ld32(o_addr + (uint32_t)(c * 32), orr);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * f);
-                        tmem_st32(o_addr + (uint32_t)(c * 32), orr);
-                    }
-                }
-                if (grow) m_ref = m_new;
-                const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
-                const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(-m_use, -m_use);
-                float2 rs2 = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int c = 0; c < 4; c += 2) {
-                    uint32_t pk[32];
-#pragma unroll
-                    for (int h = 0; h < 2; ++h)
-#pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c + h][i]), __uint_as_float(s[c + h][i + 1])), sc2, nm2);
-                            x.x = ex2_approx(x.x);
-                            x.y = ex2_approx(x.y);
-                            rs2 = __fadd2_rn(rs2, x);
-                            pk[h * 16 + (i >> 1)] = pack16(x.x, x.y, p.is_bf16);
-                        }
-                    tmem_st32(s_addr + (uint32_t)(c * 16), pk);
-                }
-                l_run += rs2.x + rs2.y;
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -322,7 +380,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     }
 }
 
-template <int D>
+template <int D, int POLY>
 static void launch_fwd_tc(const AttnPlan &a) {
     Runtime &rt = Runtime::get();
     const bool bf16 = a.dtype == KF_BFLOAT16;
@@ -337,7 +395,7 @@ static void launch_fwd_tc(const AttnPlan &a) {
     p.npairs = (int)((a.Sq + 2 * FA_BQ - 1) / (2 * FA_BQ));
     p.is_bf16 = bf16;
     constexpr int SMEM = (2 + FA_NSTAGE) * 128 * D * 2 + 256 + 1024;
-    auto kern = attn_fwd_tc_kernel<D>;
+    auto kern = attn_fwd_tc_kernel<D, POLY>;
     static bool attr_done = false;
     if (!attr_done) {
         KF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -357,8 +415,17 @@ bool launch_attention_fwd_tc(const AttnPlan &a) {
     if (a.Sq < 1 || a.Skv < 1 || a.BH < 1 || a.BH >= 65536) return false;
     auto al = [](const void *p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
     if (!al(a.q) || !al(a.k) || !al(a.v) || !al(a.out)) return false;
-    if (a.D == 64) launch_fwd_tc<64>(a);
-    else launch_fwd_tc<128>(a);
+    // share of the exponentials computed on the FMA pipe instead of the MUFU unit (tuning hook; default 3 of 8)
+    static const int poly = std::getenv("KF_ATTN_POLY") ? std::atoi(std::getenv("KF_ATTN_POLY")) : 3;
+    if (a.D == 64) {
+        if (poly <= 0) launch_fwd_tc<64, 0>(a);
+        else launch_fwd_tc<64, 3>(a);
+    } else {
+        if (poly <= 0) launch_fwd_tc<128, 0>(a);
+        else if (poly == 2) launch_fwd_tc<128, 2>(a);
+        else if (poly == 4) launch_fwd_tc<128, 4>(a);
+        else launch_fwd_tc<128, 3>(a);
+    }
     return true;
 }
 

@@ -36,6 +36,39 @@ def library_stream():
     return torch.cuda.ExternalStream(kf.stream())
 
 
+def shard_bounds(total: int, rank: int, world: int) -> tuple[int, int]:
+    """Rows / samples [lo, hi) owned by `rank` when `total` independent units are split over `world` ranks
+    (rank r owns [r*B/n, (r+1)*B/n)); the first total % world ranks take one extra unit."""
+    if not (0 <= rank < world) or total < 0:
+        raise ValueError(f"bad shard request total={total} rank={rank} world={world}")
+    base, extra = divmod(total, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def global_mean_from_partials(local_sum, local_count: int, dist):
+    """Cross-shard mean = all-reduce(sum of local sums) / all-reduce(sum of local counts) — NOT the mean of
+    per-shard means, which is wrong for unequal shards.  `local_sum` is a torch tensor on any
+    device the process group's backend supports (NCCL: cuda, gloo: cpu); it is reduced in place."""
+    import torch
+
+    cnt = torch.tensor([float(local_count)], dtype=torch.float64, device=local_sum.device)
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(local_sum)
+        dist.all_reduce(cnt)
+    return local_sum / cnt.to(local_sum.dtype)
+
+
+def average_gradients_(grads, dist) -> None:
+    """In-place sum-all-reduce of a list of torch gradient tensors followed by 1/world (data-parallel average)."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    world = dist.get_world_size()
+    for g in grads:
+        dist.all_reduce(g)
+        g.mul_(1.0 / world)
+
+
 def all_reduce_grads(params, world: int, dist) -> None:
     """sum-all-reduce every parameter gradient over the data-parallel group, then scale by 1/world."""
     import torch

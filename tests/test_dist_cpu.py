@@ -1,0 +1,67 @@
+"""N>1 host logic on CPU: world_size 2 over gloo (the GPU path uses the same functions over NCCL).
+kfunca_b200.dist imports the compiled extension at module import, but nothing here launches a kernel."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, total_rows, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from kfunca_b200.dist import average_gradients_, global_mean_from_partials, shard_bounds
+
+        rng = np.random.default_rng(7)
+        x = rng.uniform(-10, 10, (total_rows, 33))  # every rank generates the same global batch
+        lo, hi = shard_bounds(total_rows, rank, world)
+        local = x[lo:hi]
+        mean = global_mean_from_partials(torch.tensor([local.sum()], dtype=torch.float64), local.size, dist)
+        g = torch.full((5,), float(rank + 1), dtype=torch.float32)
+        average_gradients_([g], dist)
+        q.put((rank, lo, hi, float(mean.item()), g.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total_rows", [8, 7])  # equal and ragged shards
+def test_two_rank_shard_mean_and_grad_average(total_rows):
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, total_rows, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(7)
+    x = rng.uniform(-10, 10, (total_rows, 33))
+    assert res[0][1] == 0 and res[0][2] == res[1][1] and res[1][2] == total_rows  # shards tile [0, total)
+    for _, _, _, mean, g in res:
+        assert abs(mean - x.mean()) < 1e-12
+        assert g == [1.5] * 5
+
+
+def test_shard_bounds_cover_without_overlap():
+    from kfunca_b200.dist import shard_bounds
+
+    for total in (0, 1, 7, 8, 65536):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(8, 2, 2)

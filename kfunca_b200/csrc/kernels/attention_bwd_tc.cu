@@ -225,7 +225,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_con
         __syncwarp();
     } else if (warp == 8) {
         // ===================================================== MMA issuer
-        if (lane == 0 && ntile > 0) {
+        // converged warp: all lanes run the loops and waits, the elected lane issues (see umma_f16_p)
+        const bool leader = elect_one();
+        if (ntile > 0) {
             const int fmt = p.is_bf16 ? 1 : 0;
             const uint32_t idesc_t = make_idesc_f16(fmt, 0, 0, 128, 64);  // T = X Y^T : both operands K-major
             const uint32_t idesc_a = make_idesc_f16(fmt, 0, 1, 128, D);   // ACC += (TMEM) Y : B MN-major
@@ -236,9 +238,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_con
                     const uint32_t xa = x_addr + which * X_BYTES, ya = y_addr + slot * SLOT_BYTES + which * Y_BYTES;
 #pragma unroll
                     for (int kk = 0; kk < D / 16; ++kk) {
-                        umma_f16(tmem_base + (uint32_t)(set * 128 + which * 64),
-                                 make_sw128_desc(xa + (uint32_t)((kk >> 2) * X_ATOM + (kk & 3) * 32), 0, 1024),
-                                 make_sw128_desc(ya + (uint32_t)((kk >> 2) * Y_ATOM + (kk & 3) * 32), 0, 1024), idesc_t, kk ? 1u : 0u);
+                        umma_f16_p(tmem_base + (uint32_t)(set * 128 + which * 64),
+                                   make_sw128_desc(xa + (uint32_t)((kk >> 2) * X_ATOM + (kk & 3) * 32), 0, 1024),
+                                   make_sw128_desc(ya + (uint32_t)((kk >> 2) * Y_ATOM + (kk & 3) * 32), 0, 1024), idesc_t, kk ? 1u : 0u, leader);
                     }
                 }
             };
@@ -247,11 +249,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_con
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {  // K = 64 streamed rows = 4 x 16; 16-bit A in TMEM: 8 columns per step
                     if (MODE == MODE_DKV)  // dV += P^T dO_t   (B = Y1)
-                        umma_f16_ts(tmem_base + ACC0_COL, tmem_base + (uint32_t)(set * 128 + kk * 8),
-                                    make_sw128_desc(ya + Y_BYTES + kk * 2048, Y_ATOM, 1024), idesc_a, (accumulate || kk) ? 1u : 0u);
+                        umma_f16_ts_p(tmem_base + ACC0_COL, tmem_base + (uint32_t)(set * 128 + kk * 8),
+                                      make_sw128_desc(ya + Y_BYTES + kk * 2048, Y_ATOM, 1024), idesc_a, (accumulate || kk) ? 1u : 0u, leader);
                     // dK += dS^T Q_t  /  dQ += dS K_t   (B = Y0)
-                    umma_f16_ts(tmem_base + ACC1_COL, tmem_base + (uint32_t)(set * 128 + 64 + kk * 8), make_sw128_desc(ya + kk * 2048, Y_ATOM, 1024),
-                                idesc_a, (accumulate || kk) ? 1u : 0u);
+                    umma_f16_ts_p(tmem_base + ACC1_COL, tmem_base + (uint32_t)(set * 128 + 64 + kk * 8), make_sw128_desc(ya + kk * 2048, Y_ATOM, 1024),
+                                  idesc_a, (accumulate || kk) ? 1u : 0u, leader);
                 }
             };
             // ring bookkeeping: tile n (0-based) lives in slot n % NS, phase (n / NS) & 1
@@ -264,22 +266,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_con
                 const int slot = wait_slot(n);
                 tc_fence_after();
                 issue_t(n & 1, slot);
-                umma_commit(&t_full[n & 1]);
+                umma_commit_p(&t_full[n & 1], leader);
             }
             for (int n = 0; n < ntile; ++n) {
                 const int set = n & 1;
                 mbar_wait(&p_full[set], (uint32_t)((n >> 1) & 1));
                 tc_fence_after();
                 issue_acc(set, n % NS, n > 0);
-                umma_commit(&y_empty[n % NS]);  // the streamed tile n is no longer needed once these MMAs retire
+                umma_commit_p(&y_empty[n % NS], leader);  // the streamed tile n is no longer needed once these MMAs retire
                 if (n + 2 < ntile) {
                     const int slot = wait_slot(n + 2);
                     tc_fence_after();
                     issue_t(set, slot);
-                    umma_commit(&t_full[set]);
+                    umma_commit_p(&t_full[set], leader);
                 }
             }
-            umma_commit(acc_full);
+            umma_commit_p(acc_full, leader);
         }
         __syncwarp();
     } else {

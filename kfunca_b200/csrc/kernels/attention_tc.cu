@@ -246,8 +246,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         }
         __syncwarp();
       } else if (warp == 8) {
-        // ===================================================== MMA issuer
-        if (lane == 0) {
+        // ===================================================== MMA issuer (converged warp, elected lane issues: see umma_f16_p)
+        const bool leader = elect_one();
+        {
             const int fmt = p.is_bf16 ? 1 : 0;
             const uint32_t idesc_s = make_idesc_f16(fmt, 0, 0, FA_BQ, FA_BKV);
             const uint32_t idesc_pv = make_idesc_f16(fmt, 0, 1, FA_BQ, D);
@@ -256,8 +257,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 #pragma unroll
                 for (int kk = 0; kk < D / 16; ++kk) {
                     const uint32_t off = (uint32_t)((kk >> 2) * ATOM_BYTES + (kk & 3) * 32);
-                    umma_f16(tmem_base + (uint32_t)(t * 128), make_sw128_desc(q_addr + t * TILE_BYTES + off, 0, 1024),
-                             make_sw128_desc(k_addr + off, 0, 1024), idesc_s, kk ? 1u : 0u);
+                    umma_f16_p(tmem_base + (uint32_t)(t * 128), make_sw128_desc(q_addr + t * TILE_BYTES + off, 0, 1024),
+                               make_sw128_desc(k_addr + off, 0, 1024), idesc_s, kk ? 1u : 0u, leader);
                 }
             };
             auto issue_pv = [&](int t, uint32_t v_addr, bool accumulate) {
@@ -265,8 +266,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                 for (int kk = 0; kk < FA_BKV / 16; ++kk) {
                     // A = P from tensor memory: 16 k-values of 16 bits = 8 columns per step;
                     // B = V, MN-major: 16 kv rows = 2 x 1024 B per step, 64-wide d atoms ATOM_BYTES apart
-                    umma_f16_ts(tmem_base + O_COL + (uint32_t)(t * D), tmem_base + (uint32_t)(t * 128 + kk * 8),
-                                make_sw128_desc(v_addr + kk * 2048, ATOM_BYTES, 1024), idesc_pv, (accumulate || kk) ? 1u : 0u);
+                    umma_f16_ts_p(tmem_base + O_COL + (uint32_t)(t * D), tmem_base + (uint32_t)(t * 128 + kk * 8),
+                                  make_sw128_desc(v_addr + kk * 2048, ATOM_BYTES, 1024), idesc_pv, (accumulate || kk) ? 1u : 0u, leader);
                 }
             };
             int s = 0;
@@ -288,9 +289,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                 for (int t = 0; t < 2; ++t)
                     if ((t ? nblk1 : nblk0) > 0) {
                         issue_s(t, kv_addr + sk * TILE_BYTES);
-                        umma_commit(&s_full[t]);
+                        umma_commit_p(&s_full[t], leader);
                     }
-                umma_commit(&kv_empty[sk]);
+                umma_commit_p(&kv_empty[sk], leader);
             }
             for (int j = 1; j <= nmax; ++j) {
                 const int sv = next_slot();  // V_{j-1}
@@ -304,11 +305,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                         tc_fence_after();
                         issue_pv(t, kv_addr + sv * TILE_BYTES, j > 1);
                         if (j < nb_t) issue_s(t, kv_addr + sk * TILE_BYTES);
-                        umma_commit(&s_full[t]);
+                        umma_commit_p(&s_full[t], leader);
                     }
                 }
-                umma_commit(&kv_empty[sv]);
-                if (has_k) umma_commit(&kv_empty[sk]);
+                umma_commit_p(&kv_empty[sv], leader);
+                if (has_k) umma_commit_p(&kv_empty[sk], leader);
             }
         }
         __syncwarp();
@@ -415,8 +416,8 @@ bool launch_attention_fwd_tc(const AttnPlan &a) {
     if (a.Sq < 1 || a.Skv < 1 || a.BH < 1 || a.BH >= 65536) return false;
     auto al = [](const void *p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
     if (!al(a.q) || !al(a.k) || !al(a.v) || !al(a.out)) return false;
-    // share of the exponentials computed on the FMA pipe instead of the MUFU unit (tuning hook; default 3 of 8)
-    static const int poly = std::getenv("KF_ATTN_POLY") ? std::atoi(std::getenv("KF_ATTN_POLY")) : 3;
+    // share of the exponentials computed on the FMA pipe instead of the MUFU unit (tuning hook; default 0: measured slower at 2..4 of 8 while MMA issue, not MUFU, was the limiter)
+    static const int poly = std::getenv("KF_ATTN_POLY") ? std::atoi(std::getenv("KF_ATTN_POLY")) : 0;
     if (a.D == 64) {
         if (poly <= 0) launch_fwd_tc<64, 0>(a);
         else launch_fwd_tc<64, 3>(a);

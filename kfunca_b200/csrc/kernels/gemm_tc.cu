@@ -136,8 +136,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===================================================== MMA issuer
-        if (lane == 0) {
+        // ===================================================== MMA issuer (converged warp, elected lane issues: see umma_f16_p)
+        const bool leader = elect_one();
+        {
             const uint32_t idesc = make_idesc_f16(p.is_bf16 ? 1 : 0, A_MN ? 1 : 0, B_MN ? 1 : 0, G_BM, BN);
             int s = 0;
             uint32_t ph = 0;
@@ -158,10 +159,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         // MN-major: k advances by whole 8-row groups (2 x 1024 B); LBO = stride between 64-wide MN atoms
                         const uint64_t adesc = A_MN ? make_sw128_desc(sa + k * 2048, 64 * G_BK * 2, 1024) : make_sw128_desc(sa + k * 32, 0, 1024);
                         const uint64_t bdesc = B_MN ? make_sw128_desc(sb + k * 2048, 64 * G_BK * 2, 1024) : make_sw128_desc(sb + k * 32, 0, 1024);
-                        umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
+                        umma_f16_p(d_tmem, adesc, bdesc, idesc, (kb | k) ? 1u : 0u, leader);
                     }
-                    umma_commit(&empty[s]);  // stage reusable once these MMAs have read it
-                    if (kb == nkb - 1) umma_commit(&tmem_full[acc]);
+                    umma_commit_p(&empty[s], leader);  // stage reusable once these MMAs have read it
+                    if (kb == nkb - 1) umma_commit_p(&tmem_full[acc], leader);
                     if (++s == NST) {
                         s = 0;
                         ph ^= 1;

@@ -120,7 +120,7 @@ def test_attention_backward_16bit(dt, shape):
         gotf = got.float().numpy().astype(np.float64)
         scale = np.abs(exp).max()
         # 1e-6 floor: a single-key row has exactly zero dQ/dK in exact arithmetic, the kernel leaves fp32 rounding noise (~4e-8)
-            assert np.all(np.abs(gotf - exp) <= 2e-2 * np.abs(exp) + 1e-2 * scale + 1e-6), float(np.abs(gotf - exp).max() / max(scale, 1e-30))
+        assert np.all(np.abs(gotf - exp) <= 2e-2 * np.abs(exp) + 1e-2 * scale + 1e-6), float(np.abs(gotf - exp).max() / max(scale, 1e-30))
 
 
 def test_attention_backward_16bit_is_deterministic():

@@ -180,6 +180,12 @@ def run_ours(args):
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     e2e_val = world * flops / (max(e2e_ms, e2e_wall_ms) * 1e-3) / 1e12
 
+    # at N > 1 the C5 block (the only workload with a real exchange step) is timed after the headline on all ranks and
+    # attached to the same JSON line as extras.c5_block, so the driver's scaling run records it
+    block_res = None
+    if world > 1 and not args.no_extras:
+        del c_host
+        block_res = time_block(kf, Event, dist, rank, world, steps=3, warmup=3)
     if rank != 0:
         return
     # parity spot-check of the timed configuration against the oracle (a few rows, float64)
@@ -210,7 +216,75 @@ def run_ours(args):
     out["cpu_baseline"] = cpu_baseline_gemm(a_host.array.view(O.bfloat16), b_host.array.view(O.bfloat16))
     if not args.no_extras and world == 1:
         out["extras"] = extras(kf, Event, peaks)
+    if block_res is not None:
+        out["extras"] = {"c5_block": block_res}
     print(json.dumps(out))
+
+
+
+def time_block(kf, Event, dist, rank, world, steps, warmup, global_batch=8, S=4096, E=4096, H=32):
+    """C5 (BASELINE.json configs[4]): transformer block fwd+bwd, bf16, batch-sharded (global batch fixed = strong scaling);
+    the weight-gradient all-reduce and the cross-shard loss mean go through NCCL on the library stream inside the timed region."""
+    from kfunca_b200.block import Block
+    from kfunca_b200.dist import all_reduce_grads, all_reduce_mean_scalar, shard_bounds
+
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    lo, hi = shard_bounds(global_batch, rank, world)
+    bl = hi - lo
+    blk = Block(E, H, dtype=kf.bfloat16, device=local, seed=7)  # same seed on every rank = replicated weights
+    rng = np.random.default_rng(100 + rank)
+    x = kf.from_numpy(rng.uniform(-1, 1, (max(bl, 1), S, E)).astype(np.float32), local).to(kf.bfloat16)
+
+    def step():
+        loss = blk.step(x)
+        all_reduce_grads(blk.params, world, dist)
+        return all_reduce_mean_scalar(loss, world, dist)
+
+    for _ in range(max(warmup, 3)):
+        step()
+    kf.synchronize()
+    barrier(dist)
+    l0 = kf.launch_count()
+    e0, e1 = Event(), Event()
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    e1.synchronize()
+    barrier(dist)
+    launches = (kf.launch_count() - l0) // steps
+    ms = max_over_ranks(e0.elapsed_ms(e1), dist) / steps
+    flops = blk.flops_per_sample(S) * global_batch
+    lossv = float(loss.float().numpy().reshape(-1)[0])
+    return {"ms_per_step": round(ms, 3), "TFLOP/s_total": round(flops / ms / 1e9, 1), "TFLOP/s_per_gpu": round(flops / ms / 1e9 / world, 1),
+            "global_batch": global_batch, "local_batch": bl, "seq_len": S, "embed": E, "heads": H, "scaling": "strong",
+            "launches_per_step": int(launches), "loss": lossv, "finite": bool(np.isfinite(lossv)),
+            "allreduce_bytes_per_step": 2 * sum(int(p.numel()) for p in blk.params.values()) if world > 1 else 0}
+
+
+def run_block(args):
+    rank, world, dist = dist_setup(args.gpus)
+    import kfunca_b200 as kf
+    from kfunca_b200.runtime import Event
+
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    kf.set_device(local)
+    peaks = measured_peaks()
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    r = time_block(kf, Event, dist, rank, world, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    if rank != 0:
+        return
+    print(json.dumps({
+        "metric": "transformer block fwd+bwd TFLOPS (bf16, batch-sharded, NCCL grad all-reduce)", "value": r["TFLOP/s_total"], "unit": "TFLOP/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "transformer block fwd+bwd (BASELINE.json configs[4]): global batch 8, S=4096, E=4096, H=32, GLU FFN 4E; "
+                               "weights+activations >> L2", "parallelism": f"dp{world}", "detail": r},
+        "gpu_launches": r["launches_per_step"] * args.steps, "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": r["TFLOP/s_per_gpu"], "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": round(r["TFLOP/s_per_gpu"] / peaks["bf16_tflops_sustained"], 4), "traffic": None,
+                     "peak_kind": "sustained bf16 cuBLAS, " + peaks["source"], "kernel": "whole step (gemm_tc + attn_*_tc + elementwise)"}}))
 
 
 def load_traffic(kernel):
@@ -276,14 +350,28 @@ def extras(kf, Event, peaks):
     X = kf.from_numpy(rng.uniform(-1e5, 1e5, (rows, cols)).astype(np.float32), 0)
     mem("c4_topk64_8192x32768", lambda i: X.topk(k, 1, True), rows * cols * 4 + rows * k * 12, iters=5, warm=3)
     del X
-    # C3 causal attention forward bf16 B=8 H=32 S=4096 D=128
+    # C3 causal attention fwd / bwd bf16 B=8 H=32 S=4096 D=128, seeded U(-1,1); one batch entry is drawn and tiled
     Bq, H, S, D = 8, 32, 4096, 128
-    q = kf.empty([Bq, H, S, D], kf.bfloat16, 0); q.fill_(0.05)
-    kk = kf.empty([Bq, H, S, D], kf.bfloat16, 0); kk.fill_(0.03)
-    v = kf.empty([Bq, H, S, D], kf.bfloat16, 0); v.fill_(0.5)
-    ms = t(lambda i: kf.causal_attention(q, kk, v), iters=5, warm=3)
+    from oracle import oracle as O  # bf16 host dtype only
+
+    def rnd():
+        one = rng.uniform(-1, 1, (1, H, S, D)).astype(np.float32).astype(O.bfloat16)
+        return kf.from_numpy(np.ascontiguousarray(np.broadcast_to(one, (Bq, H, S, D))), 0)
+
+    q, kk, v, do = rnd(), rnd(), rnd(), rnd()
     fl = 4.0 * Bq * H * S * S * D / 2
-    res["c3_attention_fwd_bf16"] = {"ms": round(ms, 4), "TFLOP/s": round(fl / ms / 1e9, 1), "frac_of_tensor_peak": round(fl / ms / 1e9 / peaks["bf16_tflops"], 4)}
+    tp = peaks["bf16_tflops"]
+    ms_f = t(lambda i: kf.causal_attention(q, kk, v), iters=8, warm=3)
+    o, lse = kf.causal_attention_fwd(q, kk, v)
+    ms_b = t(lambda i: kf.causal_attention_bwd(do, q, kk, v, o, lse), iters=8, warm=3)
+    res["c3_attention_fwd_bf16"] = {"ms": round(ms_f, 4), "TFLOP/s": round(fl / ms_f / 1e9, 1), "frac_of_tensor_peak": round(fl / ms_f / 1e9 / tp, 4)}
+    res["c3_attention_bwd_bf16"] = {"ms": round(ms_b, 4), "TFLOP/s": round(2.5 * fl / ms_b / 1e9, 1),
+                                    "frac_of_tensor_peak": round(2.5 * fl / ms_b / 1e9 / tp, 4)}
+    res["c3_attention_fwd_bwd_bf16"] = {"ms": round(ms_f + ms_b, 4), "TFLOP/s": round(3.5 * fl / (ms_f + ms_b) / 1e9, 1),
+                                        "frac_of_tensor_peak": round(3.5 * fl / (ms_f + ms_b) / 1e9 / tp, 4)}
+    del q, kk, v, do, o, lse
+    # C5 block at one GPU (global batch 8 on this GPU); the N-GPU lines come from `--gpus N` (extras.c5_block)
+    res["c5_block_1gpu"] = time_block(kf, Event, None, 0, 1, steps=2, warmup=3)
     return res
 
 
@@ -349,9 +437,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--workload", default="gemm", choices=["gemm", "block"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "block":
+        run_block(args)
     else:
         run_ours(args)
 

@@ -95,6 +95,59 @@ def test_matmul_tc_all_layouts_and_batches(ta, tb):
         check16(out.float().numpy(), exact, mass, (ta, tb, bsz, m, k, n))
 
 
+@pytest.fixture
+def force_cta_pair():
+    os.environ["KF_GEMM_CTA_GROUP"] = "2"
+    yield
+    os.environ.pop("KF_GEMM_CTA_GROUP", None)
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+def test_matmul_tc_cta_pair_all_layouts(ta, tb, force_cta_pair):
+    """the cta_group::2 kernel (256 x 256 tiles over a CTA pair), forced on small / ragged / batched shapes"""
+    for (bsz, m, k, n) in [(1, 256, 64, 256), (1, 512, 192, 768), (3, 200, 136, 328), (2, 129, 72, 136), (1, 1000, 520, 264)]:
+        a = to16(RNG.uniform(-1, 1, (bsz, k, m) if ta else (bsz, m, k)), "bf16")
+        b = to16(RNG.uniform(-1, 1, (bsz, n, k) if tb else (bsz, k, n)), "bf16")
+        out = kf.matmul(g(a), ta, g(b), tb, 1.0)
+        af = a.astype(np.float64).transpose(0, 2, 1) if ta else a.astype(np.float64)
+        bf = b.astype(np.float64).transpose(0, 2, 1) if tb else b.astype(np.float64)
+        check16(out.float().numpy(), af @ bf, np.abs(af) @ np.abs(bf), ("pair", ta, tb, bsz, m, k, n))
+
+
+def test_gemm_tc_cta_pair_beta_fp16_and_many_tiles(force_cta_pair):
+    a, b = to16(RNG.uniform(-1, 1, (384, 128)), "fp16"), to16(RNG.uniform(-1, 1, (128, 512)), "fp16")
+    c = to16(RNG.uniform(-1, 1, (384, 512)), "fp16")
+    gc = g(c)
+    kf.gemm_out(gc, g(a), g(b), 2.0, 0.5)
+    exact = 2.0 * O.gemm(a, b) + 0.5 * c.astype(np.float64)
+    check16(gc.float().numpy(), exact, 2 * np.abs(a.astype(np.float64)) @ np.abs(b.astype(np.float64)) + 1, "pair beta")
+    # more tiles than CTA pairs: every cluster loops over several tiles, both accumulator buffers and all ring phases cycle
+    m, k, n = 2304 + 40, 1096, 5120 + 8
+    a, b = to16(RNG.uniform(-1, 1, (m, k)), "bf16"), to16(RNG.uniform(-1, 1, (k, n)), "bf16")
+    out = kf.gemm(g(a), g(b), 1.0, 0.0).float().numpy()
+    rows = [0, 127, 128, 255, 256, 1000, 2303, 2304, m - 1]
+    af, bf = a[rows].astype(np.float64), b.astype(np.float64)
+    check16(out[rows], af @ bf, np.abs(af) @ np.abs(bf), "pair rows")
+    cols = [0, 127, 128, 255, 256, 5119, 5120, n - 1]
+    af, bf = a.astype(np.float64), b[:, cols].astype(np.float64)
+    check16(out[:, cols], af @ bf, np.abs(af) @ np.abs(bf), "pair cols")
+
+
+def test_gemm_tc_default_dispatch_uses_pair_on_big_shapes():
+    """no env override: >= one wave of 256 x 256 tiles takes the pair kernel; result must match the single-CTA kernel bit for bit
+    (same k order, same fp32 accumulation)"""
+    m, k, n = 2560, 512, 2560
+    a, b = to16(RNG.uniform(-1, 1, (m, k)), "bf16"), to16(RNG.uniform(-1, 1, (k, n)), "bf16")
+    ga, gb = g(a), g(b)
+    o_default = kf.gemm(ga, gb, 1.0, 0.0).float().numpy()
+    os.environ["KF_GEMM_CTA_GROUP"] = "1"
+    try:
+        o_single = kf.gemm(ga, gb, 1.0, 0.0).float().numpy()
+    finally:
+        os.environ.pop("KF_GEMM_CTA_GROUP", None)
+    assert np.array_equal(o_default, o_single)
+
+
 def test_gemm_tc_unaligned_falls_back_to_simt():
     a, b = to16(RNG.uniform(-1, 1, (33, 77)), "bf16"), to16(RNG.uniform(-1, 1, (77, 45)), "bf16")  # ld not multiple of 8
     out = kf.gemm(g(a), g(b), 1.0, 0.0)

@@ -210,8 +210,8 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-                     "traffic": load_traffic("gemm_tc_kernel"), "peak_kind": "burst bf16 cuBLAS, " + peaks["source"],
-                     "kernel": "gemm_tc_kernel<256,false,true>"},
+                     "traffic": load_traffic("gemm_tc2_kernel"), "peak_kind": "burst bf16 cuBLAS, " + peaks["source"],
+                     "kernel": "gemm_tc2_kernel<256,false,true> (CTA pair, cta_group::2)"},
     }
     out["cpu_baseline"] = cpu_baseline_gemm(a_host.array.view(O.bfloat16), b_host.array.view(O.bfloat16))
     if not args.no_extras and world == 1:

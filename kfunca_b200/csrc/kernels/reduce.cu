@@ -42,6 +42,13 @@ struct ReduceArgs {
     int64_t factor_i;
 };
 
+// Programmatic dependent launch: let the NEXT kernel on the stream start scheduling its CTAs while this one drains, and do not
+// touch global memory before every EARLIER kernel has completed and flushed.  Both are no-ops for a launch without the attribute.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 template <typename A>
 __device__ __forceinline__ A finalize(A acc, const ReduceArgs &a) {
     if (!a.is_mean) return acc;
@@ -101,6 +108,7 @@ __device__ __forceinline__ A strided_vec_sum(const Pack<Tin, VEC> *pv, int64_t f
 template <typename Tin, typename Tout, typename A, int VEC, int W>
 __global__ void __launch_bounds__(256) reduce_rows_kernel(const ReduceArgs a) {
     __shared__ A part[8];
+    pdl_prologue();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wr = warp % W;                                  // this warp's slot inside its row
     const int64_t row = (int64_t)blockIdx.x * (8 / W) + warp / W;
@@ -156,6 +164,7 @@ template <typename Tin, typename Tout, typename A, int VEC>
 __global__ void __launch_bounds__(256) reduce_rows_split_kernel(const ReduceArgs a) {
     __shared__ A warp_part[8];
     __shared__ A cta_val;
+    pdl_prologue();
     const int s = blockIdx.x;
     const int64_t row = blockIdx.y;
     const int64_t lo = (int64_t)s * a.chunk;
@@ -216,12 +225,13 @@ __global__ void __launch_bounds__(256) reduce_rows_split_kernel(const ReduceArgs
 // LPR lanes run along `inner` (16-byte vectors), so a warp covers 32 / LPR rows per load instruction and a CTA tile is
 // LPR * VEC columns wide: narrow tiles give enough CTAs for the whole reduction to finish inside ONE 8-CTA cluster
 // (DSMEM fold, no global hand-shake) even when `inner` is only a few thousand columns.
-template <typename Tin, typename Tout, typename A, int VEC, int LPR>
+template <typename Tin, typename Tout, typename A, int VEC, int LPR, int U = 8>
 __global__ void __launch_bounds__(256) reduce_cols_kernel(const ReduceArgs a) {
     constexpr int RPW = 32 / LPR;        // rows per warp-wide load
     constexpr int PH = 8 * RPW;          // row phases per CTA
     constexpr int WIDTH = LPR * VEC;     // columns per CTA
     __shared__ A part[PH][WIDTH];
+    pdl_prologue();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int cl = lane % LPR, ph = w * RPW + lane / LPR;
     const int64_t col = ((int64_t)blockIdx.x * LPR + cl) * VEC;
@@ -236,12 +246,12 @@ __global__ void __launch_bounds__(256) reduce_cols_kernel(const ReduceArgs a) {
     if (col < a.inner) {
         const Tin *__restrict__ p = reinterpret_cast<const Tin *>(a.in) + o * a.R * a.inner + col;
         int64_t r = lo + ph;
-        for (; r + 7 * PH < hi; r += 8 * PH) {  // 8 independent 16-byte loads in flight per thread
-            Pack<Tin, VEC> pk[8];
+        for (; r + (U - 1) * PH < hi; r += U * PH) {  // U independent 16-byte loads in flight per thread
+            Pack<Tin, VEC> pk[U];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) pk[u] = ld_stream<Tin, VEC>(reinterpret_cast<const Pack<Tin, VEC> *>(p + (r + (int64_t)PH * u) * a.inner));
+            for (int u = 0; u < U; ++u) pk[u] = ld_stream<Tin, VEC>(reinterpret_cast<const Pack<Tin, VEC> *>(p + (r + (int64_t)PH * u) * a.inner));
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
+            for (int u = 0; u < U; ++u)
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) acc[j] += cvt_in<A>(pk[u].v[j]);
         }
@@ -320,6 +330,11 @@ __global__ void __launch_bounds__(256) reduce_cols_kernel(const ReduceArgs a) {
 }
 
 // ------------------------------------------------------------------ host side
+static bool pdl_enabled() {
+    const char *e = std::getenv("KF_PDL");  // default on; KF_PDL=0 switches programmatic dependent launch off
+    return !(e && e[0] == '0');
+}
+
 template <typename K>
 static void launch_clustered(K kernel, dim3 grid, dim3 cluster, const ReduceArgs &args, const char *name) {
     Runtime &rt = Runtime::get();
@@ -328,13 +343,22 @@ static void launch_clustered(K kernel, dim3 grid, dim3 cluster, const ReduceArgs
     cfg.blockDim = dim3(256);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = rt.stream();
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cluster.x;
-    attr[0].val.clusterDim.y = cluster.y;
-    attr[0].val.clusterDim.z = cluster.z;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (cluster.x * cluster.y * cluster.z > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = cluster.x;
+        attr[na].val.clusterDim.y = cluster.y;
+        attr[na].val.clusterDim.z = cluster.z;
+        ++na;
+    }
+    if (pdl_enabled()) {  // see pdl_prologue()
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = (cluster.x * cluster.y * cluster.z > 1) ? 1 : 0;
+    cfg.numAttrs = na;
     if (cluster.x * cluster.y * cluster.z > 8) {  // 16-CTA clusters are "non-portable": opt in once per kernel
         static bool opted = false;
         if (!opted) {
@@ -372,10 +396,10 @@ static void launch_rows_w(const ReduceArgs &a, int W, bool vec_ok) {
     const int64_t g = (a.rows + rows_per_cta - 1) / rows_per_cta;
     KF_CHECK(g < (int64_t)0x7FFFFFFF);
     const unsigned grid = (unsigned)g;
-#define KF_ROWS(WW)                                                                                       \
-    do {                                                                                                  \
-        if (vec_ok) reduce_rows_kernel<Tin, Tout, A, V, WW><<<grid, 256, 0, rt.stream()>>>(a);            \
-        else reduce_rows_kernel<Tin, Tout, A, 1, WW><<<grid, 256, 0, rt.stream()>>>(a);                   \
+#define KF_ROWS(WW)                                                                                                      \
+    do {                                                                                                                 \
+        if (vec_ok) launch_clustered(reduce_rows_kernel<Tin, Tout, A, V, WW>, dim3(grid), dim3(1, 1, 1), a, "reduce_rows_kernel"); \
+        else launch_clustered(reduce_rows_kernel<Tin, Tout, A, 1, WW>, dim3(grid), dim3(1, 1, 1), a, "reduce_rows_kernel");        \
     } while (0)
     switch (W) {
     case 1: KF_ROWS(1); break;
@@ -384,7 +408,7 @@ static void launch_rows_w(const ReduceArgs &a, int W, bool vec_ok) {
     default: KF_ROWS(8); break;
     }
 #undef KF_ROWS
-    rt.post_launch("reduce_rows_kernel");
+    (void)rt;
 }
 
 template <typename Tin, typename Tout, typename A>
@@ -400,6 +424,7 @@ static void reduce_rows(const void *in, void *out, int64_t rows, int64_t R, cons
     // W warps per row: as many as keep >= 8 vector loads per lane, until the grid has >= 8 CTAs per SM
     int W = 1;
     while (W < 8 && (rows + (8 / W) - 1) / (8 / W) < sms * 8 && R / (W * 2) >= (int64_t)32 * V * 8) W *= 2;
+    if (const char *e = std::getenv("KF_RED_W")) W = std::atoi(e);  // tuning hook
     const int64_t ctas = (rows + (8 / W) - 1) / (8 / W);
     if (ctas >= sms * 2 || R < (int64_t)256 * V * 16) {  // enough rows (or rows too short to split): no cross-CTA step
         launch_rows_w<Tin, Tout, A, V>(a, W, vec_ok);
@@ -457,8 +482,17 @@ static void reduce_cols(const void *in, void *out, int64_t outer, int64_t R, int
     a.partial = partial.p;
     a.counter = arrival_counters();
     dim3 grid((unsigned)tiles, (unsigned)S, (unsigned)outer), cluster(1, (unsigned)C, 1);
+    // 16 loads in flight per thread for 4-byte types with long enough chunks (more bytes in flight per SM at ~3.5 CTAs / SM)
+    bool deep = sizeof(Tin) == 4 && vec_ok && a.chunk >= (int64_t)ph * 32;
+    if (const char *e = std::getenv("KF_RED_U")) deep = deep && std::atoi(e) == 16;
 #define KF_COLS(L)                                                                                                        \
     do {                                                                                                                  \
+        if constexpr (sizeof(Tin) == 4) {                                                                                 \
+            if (deep) {                                                                                                   \
+                launch_clustered(reduce_cols_kernel<Tin, Tout, A, V, L, 16>, grid, cluster, a, "reduce_cols_kernel");     \
+                break;                                                                                                    \
+            }                                                                                                             \
+        }                                                                                                                 \
         if (vec_ok) launch_clustered(reduce_cols_kernel<Tin, Tout, A, V, L>, grid, cluster, a, "reduce_cols_kernel");     \
         else launch_clustered(reduce_cols_kernel<Tin, Tout, A, 1, L>, grid, cluster, a, "reduce_cols_kernel");            \
     } while (0)

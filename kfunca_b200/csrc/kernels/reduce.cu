@@ -329,6 +329,123 @@ __global__ void __launch_bounds__(256) reduce_cols_kernel(const ReduceArgs a) {
     }
 }
 
+
+// ------------------------------------------------------------------ columns, streaming variant (outer == 1, rows of <= 1024 vectors)
+// Every CTA owns a CONTIGUOUS band of whole rows (thread t keeps the columns of vectors t, t+256, ... in registers), so HBM sees
+// long sequential bursts instead of 256-byte pieces at a 16 KB stride; 16 independent 16-byte loads in flight per thread.
+// The grid is at most two CTAs per SM, i.e. co-resident, which makes a software grid barrier legal: partial rows go to an
+// L2-resident scratch, all CTAs meet, then CTA c folds its own slice of columns over all partials in a fixed order
+// (deterministic).  Two self-resetting counters (arrive / depart) are reused by every launch on the stream.
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <typename Tin, typename Tout, typename A, int VEC, int NVT>
+__global__ void __launch_bounds__(256) reduce_cols_stream_kernel(const ReduceArgs a) {
+    constexpr int UR = 16 / NVT;  // rows per batch: UR * NVT = 16 loads in flight
+    __shared__ A fold[256];
+    pdl_prologue();
+    const int tid = threadIdx.x;
+    const int64_t nvec = a.inner / VEC;
+    const int64_t lo = (int64_t)blockIdx.x * a.chunk;
+    int64_t hi = lo + a.chunk;
+    if (hi > a.R) hi = a.R;
+    A acc[NVT][VEC];
+#pragma unroll
+    for (int j = 0; j < NVT; ++j)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[j][i] = A(0);
+    const Pack<Tin, VEC> *__restrict__ base = reinterpret_cast<const Pack<Tin, VEC> *>(a.in);
+    int64_t r = lo;
+    for (; r + UR <= hi; r += UR) {
+        Pack<Tin, VEC> pk[UR][NVT];
+#pragma unroll
+        for (int u = 0; u < UR; ++u)
+#pragma unroll
+            for (int j = 0; j < NVT; ++j)
+                if (tid + j * 256 < nvec) pk[u][j] = ld_stream<Tin, VEC>(base + (r + u) * nvec + tid + j * 256);
+#pragma unroll
+        for (int u = 0; u < UR; ++u)
+#pragma unroll
+            for (int j = 0; j < NVT; ++j)
+                if (tid + j * 256 < nvec)
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) acc[j][i] += cvt_in<A>(pk[u][j].v[i]);
+    }
+    for (; r < hi; ++r) {
+#pragma unroll
+        for (int j = 0; j < NVT; ++j)
+            if (tid + j * 256 < nvec) {
+                Pack<Tin, VEC> pk = ld_stream<Tin, VEC>(base + r * nvec + tid + j * 256);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[j][i] += cvt_in<A>(pk.v[i]);
+            }
+    }
+    // partial row of this CTA -> scratch (stays in L2)
+    A *__restrict__ mine = reinterpret_cast<A *>(a.partial) + (int64_t)blockIdx.x * a.inner;
+#pragma unroll
+    for (int j = 0; j < NVT; ++j)
+        if (tid + j * 256 < nvec) {
+            Pack<A, VEC> out;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) out.v[i] = acc[j][i];
+            *reinterpret_cast<Pack<A, VEC> *>(mine + ((int64_t)tid + j * 256) * VEC) = out;
+        }
+    // grid barrier
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        atomicAdd(a.counter, 1u);
+        const long long t0 = clock64();
+        while (ld_acquire_u32(a.counter) < gridDim.x) {
+            if (clock64() - t0 > 4000000000ll) {
+                printf("kfunca_b200: reduce grid barrier timed out (block %d)\n", (int)blockIdx.x);
+                __trap();
+            }
+        }
+    }
+    __syncthreads();
+    // fold: this CTA owns columns [c0, c0 + cw); thread = (partial group g, column c); groups stride over the partials
+    const int P = (int)gridDim.x;
+    const int cw = (int)((a.inner + P - 1) / P);  // host guarantees cw <= 256
+    int cwp = 1;
+    while (cwp < cw) cwp <<= 1;
+    const int groups = 256 / cwp;
+    const int64_t c0 = (int64_t)blockIdx.x * cw;
+    const int c = tid % cwp, g = tid / cwp;
+    const bool live = c < cw && c0 + c < a.inner;
+    const A *__restrict__ all = reinterpret_cast<const A *>(a.partial) + c0 + c;
+    A v0 = A(0), v1 = A(0), v2 = A(0), v3 = A(0);
+    if (live) {
+        int k = g;
+        for (; k + 3 * groups < P; k += 4 * groups) {
+            v0 += __ldcg(all + (int64_t)k * a.inner);
+            v1 += __ldcg(all + (int64_t)(k + groups) * a.inner);
+            v2 += __ldcg(all + (int64_t)(k + 2 * groups) * a.inner);
+            v3 += __ldcg(all + (int64_t)(k + 3 * groups) * a.inner);
+        }
+        for (; k < P; k += groups) v0 += __ldcg(all + (int64_t)k * a.inner);
+    }
+    fold[tid] = (v0 + v1) + (v2 + v3);
+    __syncthreads();
+    if (tid < cw && c0 + tid < a.inner) {
+        A v = fold[tid];
+        for (int q = 1; q < groups; ++q) v += fold[q * cwp + tid];
+        reinterpret_cast<Tout *>(a.out)[c0 + tid] = cvt_out<Tout, A>(finalize(v, a));
+    }
+    // depart: the last CTA re-arms both counters for the next launch on the stream
+    if (tid == 0) {
+        const uint32_t t = atomicAdd(a.counter + 1, 1u);
+        if (t == gridDim.x - 1) {
+            a.counter[0] = 0;
+            a.counter[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
 // ------------------------------------------------------------------ host side
 static bool pdl_enabled() {
     const char *e = std::getenv("KF_PDL");  // default on; KF_PDL=0 switches programmatic dependent launch off
@@ -449,6 +566,47 @@ static void reduce_rows(const void *in, void *out, int64_t rows, int64_t R, cons
     else launch_clustered(reduce_rows_split_kernel<Tin, Tout, A, 1>, grid, cluster, a, "reduce_rows_split_kernel");
 }
 
+// streaming column reduce (see reduce_cols_stream_kernel); false when the shape does not qualify
+template <typename Tin, typename Tout, typename A>
+static bool reduce_cols_stream(const void *in, void *out, int64_t R, int64_t inner, const ReducePlan &pl, int64_t factor_i) {
+    constexpr int V = 16 / sizeof(Tin);
+    if (const char *e = std::getenv("KF_RED_STREAM")) {
+        if (e[0] == '0') return false;
+    }
+    if ((uintptr_t)in % 16 != 0 || inner % V != 0) return false;
+    const int64_t nvec = inner / V;
+    if (nvec < 256 || nvec > 1024) return false;                       // every thread busy, <= 4 vectors per thread per row
+    if (R * inner * (int64_t)sizeof(Tin) < (int64_t)(8 << 20)) return false;  // small problems: the cluster kernel has less fixed cost
+    Runtime &rt = Runtime::get();
+    int per_sm = 2;
+    if (const char *e = std::getenv("KF_RED_STREAM_CTAS")) per_sm = std::atoi(e);
+    int64_t G = (int64_t)rt.props().sm_count * per_sm;  // <= 2 CTAs of 256 threads per SM: always co-resident
+    if (R < G * 4) return false;
+    const int64_t chunk = (R + G - 1) / G;
+    G = (R + chunk - 1) / chunk;
+    if ((inner + G - 1) / G > 256) return false;
+    static uint32_t *counters = nullptr;
+    if (!counters) {
+        KF_CUDA(cudaMalloc(&counters, 2 * sizeof(uint32_t)));
+        rt.memset_async(counters, 0, 2 * sizeof(uint32_t));
+    }
+    ReduceArgs a{};
+    a.in = in; a.out = out; a.rows = 1; a.R = R; a.inner = inner; a.chunk = chunk;
+    a.is_mean = pl.is_mean; a.factor_f = pl.factor; a.factor_i = factor_i;
+    a.S = (int)G; a.C = 1;
+    Scratch partial(sizeof(A) * (size_t)G * (size_t)inner);
+    a.partial = partial.p;
+    a.counter = counters;
+    const int nvt = (int)((nvec + 255) / 256);
+    dim3 grid((unsigned)G), one(1, 1, 1);
+    switch (nvt) {
+    case 1: launch_clustered(reduce_cols_stream_kernel<Tin, Tout, A, V, 1>, grid, one, a, "reduce_cols_stream_kernel"); break;
+    case 2: launch_clustered(reduce_cols_stream_kernel<Tin, Tout, A, V, 2>, grid, one, a, "reduce_cols_stream_kernel"); break;
+    default: launch_clustered(reduce_cols_stream_kernel<Tin, Tout, A, V, 4>, grid, one, a, "reduce_cols_stream_kernel"); break;
+    }
+    return true;
+}
+
 template <typename Tin, typename Tout, typename A>
 static void reduce_cols(const void *in, void *out, int64_t outer, int64_t R, int64_t inner, const ReducePlan &pl, int64_t factor_i) {
     constexpr int V = 16 / sizeof(Tin);
@@ -458,6 +616,9 @@ static void reduce_cols(const void *in, void *out, int64_t outer, int64_t R, int
     a.in = in; a.out = out; a.rows = outer; a.R = R; a.inner = inner;
     a.is_mean = pl.is_mean; a.factor_f = pl.factor; a.factor_i = factor_i;
     KF_CHECK(outer <= 65535, "outer too large for the column reduce");
+    if constexpr (!std::is_same<A, int64_t>::value) {  // floating point only: integer sums keep the cluster kernel
+        if (outer == 1 && reduce_cols_stream<Tin, Tout, A>(in, out, R, inner, pl, factor_i)) return;
+    }
     const int64_t sms = Runtime::get().props().sm_count;
     // lanes per row: narrow the CTA tile (32 -> 16 -> 8 lanes, never below one 128-byte line per row for 16-byte vectors)
     // while an 8-way split — the most one cluster can fold without a global hand-shake — would leave SMs idle

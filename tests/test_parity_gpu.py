@@ -267,6 +267,38 @@ def test_reduce_shapes_and_paths(shape):
     assert abs(got[0] - arr.astype(np.float64).sum()) <= 1e-5 * np.abs(arr).astype(np.float64).sum()
 
 
+@pytest.mark.parametrize("shape,dt", [((4096, 4096), np.float32), ((3001, 2048), np.float32), ((5000, 1024), np.float32), ((2500, 1000 * 4), np.float32),
+                                      ((4096, 4096), "bf16"), ((2100, 2048), np.float16), ((4100, 1024), np.float64)])
+def test_reduce_dim0_streaming_kernel(shape, dt):
+    """outer == 1 column reduce over whole-row bands with the in-kernel grid barrier (reduce_cols_stream_kernel); called three
+    times in a row so the self-resetting arrive / depart counters are exercised, and compared with the cluster kernel"""
+    import os
+    if dt == "bf16":
+        arr = rand(shape, np.float32, -1, 1).astype(O.bfloat16)
+    elif dt == np.float16:
+        arr = rand(shape, np.float32, -1, 1).astype(np.float16)
+    else:
+        arr = rand(shape, dt)
+    t = g(arr)
+    a64 = arr.astype(np.float32).astype(np.float64) if arr.dtype.itemsize == 2 else arr.astype(np.float64)
+    mass = np.abs(a64).sum(axis=0, keepdims=True)
+    tol = 1e-5 if dt == np.float32 else (1e-12 if dt == np.float64 else 4e-3)  # 16-bit: one output rounding
+    for op in ("sum", "mean", "sum"):
+        got_t = getattr(t, op)(0)
+        got = got_t.float().numpy().astype(np.float64) if arr.dtype.itemsize == 2 else got_t.numpy().astype(np.float64)
+        exact = a64.sum(0, keepdims=True) / (shape[0] if op == "mean" else 1)
+        m = mass / (shape[0] if op == "mean" else 1)
+        assert got.shape == exact.shape
+        assert np.all(np.abs(got - exact) <= tol * np.maximum(m, 1e-30)), (shape, dt, op, float(np.abs(got - exact).max()))
+    os.environ["KF_RED_STREAM"] = "0"
+    try:
+        other = t.sum(0)
+    finally:
+        os.environ.pop("KF_RED_STREAM", None)
+    o = other.float().numpy().astype(np.float64) if arr.dtype.itemsize == 2 else other.numpy().astype(np.float64)
+    assert np.all(np.abs(o - a64.sum(0, keepdims=True)) <= tol * mass)
+
+
 def test_reduce_other_dtypes():
     arr = rand((37, 513), np.float64)
     assert_close(g(arr).sum(1), arr.sum(1, keepdims=True), rtol=1e-12, atol=1e-9)

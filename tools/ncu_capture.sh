@@ -5,7 +5,7 @@ set -u
 tag=$1; shift
 fams=${@:-"ew reduce permute topk gemm attn"}
 mkdir -p gpurun_out
-declare -A KRE=( [ew]="ew_" [reduce]="reduce_" [permute]="transpose_" [topk]="topk_" [gemm]="gemm_tc" [attn]="attn_fwd_tc" [attn_bwd]="attn_bwd" )
+declare -A KRE=( [ew]="ew_" [reduce]="reduce_" [permute]="transpose_" [topk]="topk_" [gemm]="gemm_tc2" [attn]="attn_fwd_tc" [attn_bwd]="attn_bwd" )
 declare -A CNT=( [ew]=2 [reduce]=5 [permute]=1 [topk]=2 [gemm]=1 [attn]=1 [attn_bwd]=3 )
 for f in $fams; do
   out=gpurun_out/${tag}_${f}

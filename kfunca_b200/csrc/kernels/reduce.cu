@@ -343,7 +343,7 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
 }
 
 template <typename Tin, typename Tout, typename A, int VEC, int NVT>
-__global__ void __launch_bounds__(256) reduce_cols_stream_kernel(const ReduceArgs a) {
+__global__ void __launch_bounds__(256, 2) reduce_cols_stream_kernel(const ReduceArgs a) {
     constexpr int UR = 16 / NVT;  // rows per batch: UR * NVT = 16 loads in flight
     __shared__ A fold[256];
     pdl_prologue();
@@ -578,9 +578,24 @@ static bool reduce_cols_stream(const void *in, void *out, int64_t R, int64_t inn
     if (nvec < 256 || nvec > 1024) return false;                       // every thread busy, <= 4 vectors per thread per row
     if (R * inner * (int64_t)sizeof(Tin) < (int64_t)(8 << 20)) return false;  // small problems: the cluster kernel has less fixed cost
     Runtime &rt = Runtime::get();
+    const int nvt = (int)((nvec + 255) / 256);
+    // the grid barrier needs every CTA resident at once: ask the driver how many CTAs of THIS instantiation fit on an SM
+    // (register / shared-memory limits differ per dtype) and never launch more than that
+    static int occ_cache[3] = {-1, -1, -1};
+    const int oi = nvt == 1 ? 0 : (nvt == 2 ? 1 : 2);
+    if (occ_cache[oi] < 0) {
+        int occ = 0;
+        const void *fn = nvt == 1 ? (const void *)reduce_cols_stream_kernel<Tin, Tout, A, V, 1>
+                       : nvt == 2 ? (const void *)reduce_cols_stream_kernel<Tin, Tout, A, V, 2>
+                                  : (const void *)reduce_cols_stream_kernel<Tin, Tout, A, V, 4>;
+        KF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 256, 0));
+        occ_cache[oi] = occ;
+    }
     int per_sm = 2;
     if (const char *e = std::getenv("KF_RED_STREAM_CTAS")) per_sm = std::atoi(e);
-    int64_t G = (int64_t)rt.props().sm_count * per_sm;  // <= 2 CTAs of 256 threads per SM: always co-resident
+    if (per_sm > occ_cache[oi]) per_sm = occ_cache[oi];
+    if (per_sm < 1) return false;
+    int64_t G = (int64_t)rt.props().sm_count * per_sm;  // co-resident by construction
     if (R < G * 4) return false;
     const int64_t chunk = (R + G - 1) / G;
     G = (R + chunk - 1) / chunk;
@@ -597,7 +612,6 @@ static bool reduce_cols_stream(const void *in, void *out, int64_t R, int64_t inn
     Scratch partial(sizeof(A) * (size_t)G * (size_t)inner);
     a.partial = partial.p;
     a.counter = counters;
-    const int nvt = (int)((nvec + 255) / 256);
     dim3 grid((unsigned)G), one(1, 1, 1);
     switch (nvt) {
     case 1: launch_clustered(reduce_cols_stream_kernel<Tin, Tout, A, V, 1>, grid, one, a, "reduce_cols_stream_kernel"); break;

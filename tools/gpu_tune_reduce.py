@@ -25,7 +25,7 @@ def t(fn, iters=50, warm=5):
 
 
 def setenv(d):
-    for k in ("KF_RED_S", "KF_RED_C", "KF_RED_LPR", "KF_RED_U", "KF_RED_W", "KF_PDL"):
+    for k in ("KF_RED_S", "KF_RED_C", "KF_RED_LPR", "KF_RED_U", "KF_RED_W", "KF_PDL", "KF_RED_STREAM", "KF_RED_STREAM_CTAS"):
         os.environ.pop(k, None)
     for k, v in d.items():
         os.environ[k] = str(v)
@@ -36,13 +36,18 @@ for pdl in (1, 0):
     print("== PDL", pdl)
     setenv({"KF_PDL": pdl})
     print("defaults: sum0 %.2f  sum1 %.2f  sumall %.2f us" % (t(lambda i: A[i].sum(0)), t(lambda i: A[i].sum(1)), t(lambda i: flat[i].sum(0))), flush=True)
+    for st in (0, 1, 2):
+        setenv({"KF_PDL": pdl, "KF_RED_STREAM": 1 if st else 0, "KF_RED_STREAM_CTAS": max(st, 1)})
+        ok = np.allclose(A[0].sum(0).numpy(), ref.sum(0, keepdims=True), rtol=1e-4, atol=1e-2)
+        print("  cols stream=%d ctas/sm=%d: sum0 %.2f us  mean0 %.2f us ok=%s" % (1 if st else 0, max(st, 1), t(lambda i: A[i].sum(0)), t(lambda i: A[i].mean(0)), ok), flush=True)
+    setenv({"KF_PDL": pdl, "KF_RED_STREAM": 0})
     for W in (2, 4, 8):
         setenv({"KF_PDL": pdl, "KF_RED_W": W})
         ok = np.allclose(A[0].sum(1).numpy(), ref.sum(1, keepdims=True), rtol=1e-4, atol=1e-2)
         print("  rows W=%d: sum1 %.2f us ok=%s" % (W, t(lambda i: A[i].sum(1)), ok), flush=True)
-    for (S, C, L) in [(8, 8, 16), (8, 8, 8), (8, 8, 32), (16, 8, 16), (16, 8, 8), (16, 16, 16), (16, 16, 8), (4, 4, 8), (16, 16, 32), (32, 8, 32), (8, 4, 16), (8, 1, 16), (16, 1, 32)]:
+    for (S, C, L) in [(8, 8, 16), (8, 8, 8), (8, 8, 32), (16, 8, 16), (16, 16, 16), (16, 16, 8), (32, 8, 32), (8, 1, 16)]:
         for U in (8, 16):
-            setenv({"KF_PDL": pdl, "KF_RED_S": S, "KF_RED_C": C, "KF_RED_LPR": L, "KF_RED_U": U})
+            setenv({"KF_PDL": pdl, "KF_RED_STREAM": 0, "KF_RED_S": S, "KF_RED_C": C, "KF_RED_LPR": L, "KF_RED_U": U})
             try:
                 ok = np.allclose(A[0].sum(0).numpy(), ref.sum(0, keepdims=True), rtol=1e-4, atol=1e-2)
                 print("  cols S=%d C=%d L=%d U=%d: sum0 %.2f us ok=%s" % (S, C, L, U, t(lambda i: A[i].sum(0)), ok), flush=True)

@@ -185,7 +185,7 @@ def run_ours(args):
     block_res = None
     if world > 1 and not args.no_extras:
         del c_host
-        block_res = time_block(kf, Event, dist, rank, world, steps=3, warmup=3)
+        block_res = time_block(kf, Event, dist, rank, world, steps=5, warmup=3)
     if rank != 0:
         return
     # parity spot-check of the timed configuration against the oracle (a few rows, float64)
@@ -211,7 +211,7 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
                      "traffic": load_traffic("gemm_tc2_kernel"), "peak_kind": "burst bf16 cuBLAS, " + peaks["source"],
-                     "kernel": "gemm_tc2_kernel<256,false,true> (CTA pair, cta_group::2)"},
+                     "kernel": "gemm_tc2_kernel<256,false,false> (CTA pair, cta_group::2)"},
     }
     out["cpu_baseline"] = cpu_baseline_gemm(a_host.array.view(O.bfloat16), b_host.array.view(O.bfloat16))
     if not args.no_extras and world == 1:
@@ -245,19 +245,21 @@ def time_block(kf, Event, dist, rank, world, steps, warmup, global_batch=8, S=40
     kf.synchronize()
     barrier(dist)
     l0 = kf.launch_count()
-    e0, e1 = Event(), Event()
-    e0.record()
-    for _ in range(steps):
+    marks = [Event() for _ in range(steps + 1)]  # one event per step boundary: the total is what is reported, the per-step
+    marks[0].record()                            # spread (min / max) shows power-cap drift or a one-off stall
+    for i in range(steps):
         loss = step()
-    e1.record()
-    e1.synchronize()
+        marks[i + 1].record()
+    marks[-1].synchronize()
     barrier(dist)
     launches = (kf.launch_count() - l0) // steps
-    ms = max_over_ranks(e0.elapsed_ms(e1), dist) / steps
+    per_step = [marks[i].elapsed_ms(marks[i + 1]) for i in range(steps)]
+    ms = max_over_ranks(marks[0].elapsed_ms(marks[-1]), dist) / steps
     flops = blk.flops_per_sample(S) * global_batch
     lossv = float(loss.float().numpy().reshape(-1)[0])
     return {"ms_per_step": round(ms, 3), "TFLOP/s_total": round(flops / ms / 1e9, 1), "TFLOP/s_per_gpu": round(flops / ms / 1e9 / world, 1),
             "global_batch": global_batch, "local_batch": bl, "seq_len": S, "embed": E, "heads": H, "scaling": "strong",
+            "ms_step_min": round(min(per_step), 3), "ms_step_max": round(max(per_step), 3),
             "launches_per_step": int(launches), "loss": lossv, "finite": bool(np.isfinite(lossv)),
             "allreduce_bytes_per_step": 2 * sum(int(p.numel()) for p in blk.params.values()) if world > 1 else 0}
 
@@ -371,7 +373,7 @@ def extras(kf, Event, peaks):
                                         "frac_of_tensor_peak": round(3.5 * fl / (ms_f + ms_b) / 1e9 / tp, 4)}
     del q, kk, v, do, o, lse
     # C5 block at one GPU (global batch 8 on this GPU); the N-GPU lines come from `--gpus N` (extras.c5_block)
-    res["c5_block_1gpu"] = time_block(kf, Event, None, 0, 1, steps=2, warmup=3)
+    res["c5_block_1gpu"] = time_block(kf, Event, None, 0, 1, steps=5, warmup=3)
     return res
 
 

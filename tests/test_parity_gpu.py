@@ -284,17 +284,25 @@ def test_reduce_dim0_streaming_kernel(shape, dt):
     mass = np.abs(a64).sum(axis=0, keepdims=True)
     tol = 1e-5 if dt == np.float32 else (1e-12 if dt == np.float64 else 4e-3)  # 16-bit: one output rounding
     for op in ("sum", "mean", "sum"):
-        got_t = getattr(t, op)(0)
+        os.environ["KF_RED_STREAM"] = "1"  # opt-in variant (the cluster kernel is the default)
+        try:
+            got_t = getattr(t, op)(0)
+        finally:
+            os.environ.pop("KF_RED_STREAM", None)
         got = got_t.float().numpy().astype(np.float64) if arr.dtype.itemsize == 2 else got_t.numpy().astype(np.float64)
         exact = a64.sum(0, keepdims=True) / (shape[0] if op == "mean" else 1)
         m = mass / (shape[0] if op == "mean" else 1)
         assert got.shape == exact.shape
         assert np.all(np.abs(got - exact) <= tol * np.maximum(m, 1e-30)), (shape, dt, op, float(np.abs(got - exact).max()))
-    os.environ["KF_RED_STREAM"] = "0"
+    other = t.sum(0)  # default: cluster kernel with the push fold
+    os.environ["KF_RED_PUSH"] = "0"
     try:
-        other = t.sum(0)
+        pull = t.sum(0)  # cluster kernel, pull fold (cluster.sync + remote reads)
     finally:
-        os.environ.pop("KF_RED_STREAM", None)
+        os.environ.pop("KF_RED_PUSH", None)
+    pl = pull.float().numpy() if arr.dtype.itemsize == 2 else pull.numpy()
+    ot = other.float().numpy() if arr.dtype.itemsize == 2 else other.numpy()
+    assert np.array_equal(pl, ot)  # same summation order: bit-identical
     o = other.float().numpy().astype(np.float64) if arr.dtype.itemsize == 2 else other.numpy().astype(np.float64)
     assert np.all(np.abs(o - a64.sum(0, keepdims=True)) <= tol * mass)
 

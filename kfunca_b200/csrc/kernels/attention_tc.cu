@@ -26,7 +26,6 @@ constexpr int FA_BQ = 128, FA_BKV = 128;
 // warps 0-3 softmax(tile 0), 4-7 softmax(tile 1), 8 MMA issuer, 9 TMA producer, 10-11 idle.  12 warps = 3 whole warpgroups so that
 // setmaxnreg can move registers from the control warpgroup (40 / thread) to the two softmax warpgroups (232 / thread): a
 // softmax thread holds a whole 128-column S row plus the packed P chunk, which does not fit the 168 the launch gives everyone.
-constexpr int FA_THREADS = 384;
 constexpr int FA_NSTAGE = 4;     // K/V ring slots (K_0, V_0, K_1, V_1, ... in consumption order)
 
 struct AttnTcParams {
@@ -92,26 +91,32 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
 }
 
 
-// Softmax of one 128-key block for one thread (= one query row): S row from tensor memory, [mask], row max, lazy
-// rescale of O / l, P = exp2(S c - m) written back over S as 16-bit, running row sum.  `lim`: columns > lim are masked.
-// POLY: of every 8 column pairs, this many take the FMA-pipe exp2
-template <int D, bool BF16, bool MASKED, int POLY>
-__device__ __forceinline__ void fwd_softmax_block(const uint32_t s_addr, const uint32_t o_addr, const float sc, const int lim, const bool first,
-                                                  float &m_ref, float &l_run) {
-    uint32_t s[4][32];
+// Softmax of one 128-key block for one thread.  NH = 1 (default): thread = one query row (128 columns).  NH = 2 (experiment): TWO
+// threads per row (warps w and w + 4 of the tile own columns [0, 64) and [64, 128)), so every dependent step (TMEM load, max
+// tree, exp, TMEM store) is half as long.  The halves agree on the row maximum through shared memory and one 64-thread named
+// barrier per block; that barrier also orders "both halves have loaded S" before either overwrites S with P.
+// S row from tensor memory, [mask], row max, lazy rescale of O / l, P = exp2(S c - m) written back over S as 16-bit, running
+// row sum (per half).  `lim`: columns > lim (relative to this half) are masked.  POLY: of every 8 column pairs, this many take
+// the FMA-pipe exp2.
+template <int D, bool BF16, bool MASKED, int POLY, int NH>
+__device__ __forceinline__ void fwd_softmax_block(const uint32_t s_addr, const uint32_t p_addr, const uint32_t o_addr, const float sc, const int lim,
+                                                  const bool first, float &m_ref, float &l_run, float *xch_mine, const float *xch_peer,
+                                                  const int bar_id) {
+    constexpr int NC = 4 / NH;  // 32-column chunks per thread
+    uint32_t s[NC][32];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) tmem_ld32(s_addr + (uint32_t)(c * 32), s[c]);
+    for (int c = 0; c < NC; ++c) tmem_ld32(s_addr + (uint32_t)(c * 32), s[c]);
     tmem_ld_wait();
     if (MASKED) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < NC; ++c)
 #pragma unroll
             for (int i = 0; i < 32; ++i)
                 if (c * 32 + i > lim) s[c][i] = 0xff800000u;  // -inf
     }
     float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int c = 0; c < NC; ++c)
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
             mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
@@ -119,14 +124,20 @@ __device__ __forceinline__ void fwd_softmax_block(const uint32_t s_addr, const u
             mx2 = fmaxf(mx2, fmaxf(__uint_as_float(s[c][i + 4]), __uint_as_float(s[c][i + 5])));
             mx3 = fmaxf(mx3, fmaxf(__uint_as_float(s[c][i + 6]), __uint_as_float(s[c][i + 7])));
         }
-    const float m_new = fmaxf(m_ref, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc);
+    float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+    if (NH == 2) {
+        *xch_mine = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        mx = fmaxf(mx, *xch_peer);
+    }
+    const float m_new = fmaxf(m_ref, mx * sc);
     // lazy reference max: only move it (and rescale O, l) when the row max grew by more than 2^8
     const bool grow = first ? true : (m_new - m_ref > 8.f);
     if (!first && __any_sync(0xffffffffu, grow)) {
         const float f = grow ? ((m_ref == -INFINITY) ? 0.f : ex2_approx(m_ref - m_new)) : 1.f;
         l_run *= f;
 #pragma unroll 1
-        for (int c = 0; c < D / 32; ++c) {
+        for (int c = 0; c < D / 32 / NH; ++c) {
             uint32_t orr[32];
             tmem_ld32(o_addr + (uint32_t)(c * 32), orr);
             tmem_ld_wait();
@@ -138,9 +149,9 @@ __device__ __forceinline__ void fwd_softmax_block(const uint32_t s_addr, const u
     if (grow) m_ref = m_new;
     const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
     const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(-m_use, -m_use);
-    float2 rs2 = make_float2(0.f, 0.f);
+    float2 rs2 = make_float2(0.f, 0.f), rs3 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int c = 0; c < 4; c += 2) {
+    for (int c = 0; c < NC; c += 2) {
         uint32_t pk[32];
 #pragma unroll
         for (int h = 0; h < 2; ++h)
@@ -153,26 +164,39 @@ __device__ __forceinline__ void fwd_softmax_block(const uint32_t s_addr, const u
                     x.x = ex2_approx(x.x);
                     x.y = ex2_approx(x.y);
                 }
-                rs2 = __fadd2_rn(rs2, x);
+                if (i & 2) rs3 = __fadd2_rn(rs3, x);  // two accumulators: half the dependent-add chain
+                else rs2 = __fadd2_rn(rs2, x);
                 pk[h * 16 + (i >> 1)] = pack16t<BF16>(x);
             }
-        tmem_st32(s_addr + (uint32_t)(c * 16), pk);
+        tmem_st32(p_addr + (uint32_t)(c * 16), pk);
     }
-    l_run += rs2.x + rs2.y;
+    l_run += (rs2.x + rs2.y) + (rs3.x + rs3.y);
 }
 
 // One CTA = two 128-row query tiles (a 256-row "pair") of one (batch, head); the two tiles ping-pong on the
 // tensor pipe: while softmax warps work on S of tile t, the MMA warp runs P V + the next Q K^T of tile 1-t.
-template <int D, int POLY>
-__global__ void __launch_bounds__(FA_THREADS, 1)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                   const __grid_constant__ CUtensorMap tmap_v, const AttnTcParams p) {
+// Warp roles: [0, 8 NH) softmax (tile = w / (4 NH), column half = (w / 4) % NH, TMEM lane quarter = w % 4), then the MMA issuer,
+// the TMA producer and two idle warps that complete the control warpgroup (setmaxnreg works on whole warpgroups).
+template <int NH>
+struct FaCfg {
+    static constexpr int NSW = 8 * NH;             // softmax warps
+    static constexpr int THREADS = (NSW + 4) * 32;  // 384 (NH = 1) or 640 (NH = 2): whole warpgroups, setmaxnreg moves registers
+    // NH = 1: launch at 168, control warpgroup 88, softmax 208 (a thread holds a whole 128-column S row).
+    // NH = 2: launch at 96 (640 threads), control warpgroup 64 (frees 128 x 32), the four softmax warpgroups 104 (takes 512 x 8).
+    static constexpr int REG_CTRL = NH == 1 ? 88 : 64;
+    static constexpr int REG_SOFTMAX = NH == 1 ? 208 : 104;
+};
+
+template <int D, int POLY, int NH>
+__device__ __forceinline__ void attn_fwd_tc_body(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, const CUtensorMap &tmap_v,
+                                                 const AttnTcParams &p) {
     constexpr int ATOMS = D / 64;              // 64-element (128 B) swizzle atoms along the head dimension
     constexpr int TILE_BYTES = 128 * D * 2;    // one 128 x D 16-bit tile
     constexpr int ATOM_BYTES = 128 * 128;      // 128 rows x 128 B
     constexpr uint32_t TMEM_COLS = 512;        // S0 | S1 | O0 | O1 (P_t aliases the first 64 columns of S_t)
     constexpr uint32_t O_COL = 256;
     constexpr int NS = FA_NSTAGE;
+    constexpr int NSW = FaCfg<NH>::NSW, W_MMA = NSW, W_TMA = NSW + 1;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char *sQ = smem;                    // 2 tiles
@@ -183,6 +207,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     uint64_t *s_full = bars + 1 + 2 * NS;  // [2]
     uint64_t *p_full = s_full + 2;         // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(p_full + 2);
+    float *xch = reinterpret_cast<float *>(smem + (2 + NS) * TILE_BYTES + 256);  // [tile][half][parity][row] row-max / row-sum exchange (NH = 2)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bh = blockIdx.x / p.npairs;
@@ -196,7 +221,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const int nblk0 = blocks_of(0), nblk1 = blocks_of(1);  // scalars: a dynamically indexed local array would live in local memory
     const int nmax = max(nblk0, nblk1);
 
-    if (warp == 9 && lane == 0) {
+    if (warp == W_TMA && lane == 0) {
         prefetch_tmap(&tmap_q);
         prefetch_tmap(&tmap_k);
         prefetch_tmap(&tmap_v);
@@ -207,21 +232,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         }
         for (int t = 0; t < 2; ++t) {
             mbar_init(&s_full[t], 1);
-            mbar_init(&p_full[t], 4);
+            mbar_init(&p_full[t], 4 * NH);
         }
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == W_MMA) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= 8) {
-      // control warpgroup (warps 10-11 idle): the register hand-over must sit INSIDE the role branch, ptxas budgets the
+    if (warp >= NSW) {
+      // control warpgroup (last two warps idle): the register hand-over must sit INSIDE the role branch, ptxas budgets the
       // code that follows a setmaxnreg by the value it names
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-      if (warp == 9) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FaCfg<NH>::REG_CTRL));
+      if (warp == W_TMA) {
         // ===================================================== TMA producer
         if (lane == 0) {
             const int ntile_q = nblk1 > 0 ? 2 : 1;
@@ -245,7 +270,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             }
         }
         __syncwarp();
-      } else if (warp == 8) {
+      } else if (warp == W_MMA) {
         // ===================================================== MMA issuer (converged warp, elected lane issues: see umma_f16_p)
         const bool leader = elect_one();
         {
@@ -315,17 +340,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         __syncwarp();
       }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
-        // ===================================================== softmax + epilogue: thread = one query row of tile t
-        const int t = warp >> 2, q = warp & 3;
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FaCfg<NH>::REG_SOFTMAX));
+        // ===================================================== softmax + epilogue: thread = one query row (or half of it) of tile t
+        const int t = warp / (4 * NH), h = (warp >> 2) % NH, q = warp & 3;
         const int n_t = t ? nblk1 : nblk0;
         if (n_t > 0) {
+            constexpr int HC = 128 / NH;   // S columns per thread
+            constexpr int HD = D / NH;     // O columns per thread
             const int r = q * 32 + lane;
             const int64_t q0t = (int64_t)q0 + t * FA_BQ;
             const int64_t m_row = q0t + r;
             const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-            const uint32_t s_addr = lane_addr + (uint32_t)(t * 128);
-            const uint32_t o_addr = lane_addr + O_COL + (uint32_t)(t * D);
+            const uint32_t s_addr = lane_addr + (uint32_t)(t * 128 + h * HC);
+            const uint32_t p_addr = lane_addr + (uint32_t)(t * 128 + h * (HC / 2));
+            const uint32_t o_addr = lane_addr + O_COL + (uint32_t)(t * D + h * HD);
+            float *xm = xch + ((t * 2 + h) * 2) * 128 + r;        // [parity] stride 128
+            const float *xp = xch + ((t * 2 + (h ^ 1)) * 2) * 128 + r;
+            const int bar_id = 1 + t * 4 + q;                      // named barrier of this row quarter's two half-warps
             const float sc = p.scale_log2;
             float m_ref = -INFINITY, l_run = 0.f;
             for (int j = 0; j < n_t; ++j) {
@@ -333,14 +364,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                 mbar_wait(&s_full[t], (uint32_t)(j & 1));
                 tc_fence_after();
                 const bool masked = (kv0 + FA_BKV - 1 > q0t) || (kv0 + FA_BKV > p.Skv);  // diagonal / ragged block (CTA-uniform per tile)
-                const int64_t lim64 = min(m_row, p.Skv - 1) - kv0;                      // columns i > lim are masked
+                const int64_t lim64 = min(m_row, p.Skv - 1) - kv0 - h * HC;             // columns i > lim (of this half) are masked
                 const int lim = (int)max((int64_t)-1, min(lim64, (int64_t)127));
+                float *xm_j = xm + (j & 1) * 128;
+                const float *xp_j = xp + (j & 1) * 128;
                 if (p.is_bf16) {
-                    if (masked) fwd_softmax_block<D, true, true, POLY>(s_addr, o_addr, sc, lim, j == 0, m_ref, l_run);
-                    else fwd_softmax_block<D, true, false, POLY>(s_addr, o_addr, sc, lim, j == 0, m_ref, l_run);
+                    if (masked) fwd_softmax_block<D, true, true, POLY, NH>(s_addr, p_addr, o_addr, sc, lim, j == 0, m_ref, l_run, xm_j, xp_j, bar_id);
+                    else fwd_softmax_block<D, true, false, POLY, NH>(s_addr, p_addr, o_addr, sc, lim, j == 0, m_ref, l_run, xm_j, xp_j, bar_id);
                 } else {
-                    if (masked) fwd_softmax_block<D, false, true, POLY>(s_addr, o_addr, sc, lim, j == 0, m_ref, l_run);
-                    else fwd_softmax_block<D, false, false, POLY>(s_addr, o_addr, sc, lim, j == 0, m_ref, l_run);
+                    if (masked) fwd_softmax_block<D, false, true, POLY, NH>(s_addr, p_addr, o_addr, sc, lim, j == 0, m_ref, l_run, xm_j, xp_j, bar_id);
+                    else fwd_softmax_block<D, false, false, POLY, NH>(s_addr, p_addr, o_addr, sc, lim, j == 0, m_ref, l_run, xm_j, xp_j, bar_id);
                 }
                 tmem_st_wait();
                 tc_fence_before();
@@ -348,13 +381,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                 if (lane == 0) mbar_arrive(&p_full[t]);
             }
             // ---- epilogue: O / l -> 16-bit -> global, row LSE
+            if (NH == 2) {  // total row sum = sum of the two halves (slot parity n_t: the last block used parity (n_t - 1) & 1)
+                xm[(n_t & 1) * 128] = l_run;
+                asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+                l_run += xp[(n_t & 1) * 128];
+            }
             mbar_wait(&s_full[t], (uint32_t)(n_t & 1));
             tc_fence_after();
             const float inv_l = 1.f / l_run;
             const bool row_ok = m_row < p.Sq;
-            uint16_t *orow = reinterpret_cast<uint16_t *>(p.out) + ((int64_t)bh * p.Sq + (row_ok ? m_row : 0)) * D;
+            uint16_t *orow = reinterpret_cast<uint16_t *>(p.out) + ((int64_t)bh * p.Sq + (row_ok ? m_row : 0)) * D + h * HD;
 #pragma unroll 1
-            for (int c = 0; c < D / 32; ++c) {
+            for (int c = 0; c < HD / 32; ++c) {
                 uint32_t orr[32];
                 tmem_ld32(o_addr + (uint32_t)(c * 32), orr);  // .sync.aligned: every lane takes part, only the stores are predicated
                 tmem_ld_wait();
@@ -370,18 +408,31 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                     }
                 }
             }
-            if (row_ok && p.lse) p.lse[(int64_t)bh * p.Sq + m_row] = (m_ref + log2f(l_run)) * 0.6931471805599453f;
+            if (h == 0 && row_ok && p.lse) p.lse[(int64_t)bh * p.Sq + m_row] = (m_ref + log2f(l_run)) * 0.6931471805599453f;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == W_MMA) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
 template <int D, int POLY>
+__global__ void __launch_bounds__(FaCfg<1>::THREADS, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                   const __grid_constant__ CUtensorMap tmap_v, const AttnTcParams p) {
+    attn_fwd_tc_body<D, POLY, 1>(tmap_q, tmap_k, tmap_v, p);
+}
+template <int D, int POLY>
+__global__ void __launch_bounds__(FaCfg<2>::THREADS, 1)
+attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                    const __grid_constant__ CUtensorMap tmap_v, const AttnTcParams p) {
+    attn_fwd_tc_body<D, POLY, 2>(tmap_q, tmap_k, tmap_v, p);
+}
+
+template <int D, int POLY, int NH>
 static void launch_fwd_tc(const AttnPlan &a) {
     Runtime &rt = Runtime::get();
     const bool bf16 = a.dtype == KF_BFLOAT16;
@@ -395,8 +446,10 @@ static void launch_fwd_tc(const AttnPlan &a) {
     p.scale_log2 = (float)(1.4426950408889634 / std::sqrt((double)D));
     p.npairs = (int)((a.Sq + 2 * FA_BQ - 1) / (2 * FA_BQ));
     p.is_bf16 = bf16;
-    constexpr int SMEM = (2 + FA_NSTAGE) * 128 * D * 2 + 256 + 1024;
-    auto kern = attn_fwd_tc_kernel<D, POLY>;
+    constexpr int SMEM = (2 + FA_NSTAGE) * 128 * D * 2 + 256 + 4096 + 1024;  // tiles + barriers + max/sum exchange + alignment slack
+    void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnTcParams);
+    if constexpr (NH == 1) kern = attn_fwd_tc_kernel<D, POLY>;
+    else kern = attn_fwd_tc2_kernel<D, POLY>;
     static bool attr_done = false;
     if (!attr_done) {
         KF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -404,8 +457,8 @@ static void launch_fwd_tc(const AttnPlan &a) {
     }
     const int64_t grid = a.BH * p.npairs;
     KF_CHECK(grid < (int64_t)0x7FFFFFFF);
-    kern<<<(unsigned)grid, FA_THREADS, SMEM, rt.stream()>>>(tq, tk, tv, p);
-    rt.post_launch("attn_fwd_tc_kernel");
+    kern<<<(unsigned)grid, FaCfg<NH>::THREADS, SMEM, rt.stream()>>>(tq, tk, tv, p);
+    rt.post_launch(NH == 1 ? "attn_fwd_tc_kernel" : "attn_fwd_tc2_kernel");
 }
 
 bool launch_attention_fwd_tc(const AttnPlan &a) {
@@ -418,15 +471,25 @@ bool launch_attention_fwd_tc(const AttnPlan &a) {
     if (!al(a.q) || !al(a.k) || !al(a.v) || !al(a.out)) return false;
     // share of the exponentials computed on the FMA pipe instead of the MUFU unit (tuning hook; default 0: measured slower at 2..4 of 8 while MMA issue, not MUFU, was the limiter)
     static const int poly = std::getenv("KF_ATTN_POLY") ? std::atoi(std::getenv("KF_ATTN_POLY")) : 0;
+    // threads per query row in the softmax (see fwd_softmax_block).  Measured at C3: one thread per row 1.08 ms (1017 TFLOP/s), two
+    // threads per row 1.34 ms (818 TFLOP/s) — the extra named barrier, doubled polling and 96-register budget cost more than the
+    // shorter dependent chains gain, so KF_ATTN_SPLIT=2 stays an opt-in experiment
+    static const int nh = std::getenv("KF_ATTN_SPLIT") ? std::atoi(std::getenv("KF_ATTN_SPLIT")) : 1;
+#define KF_FWD(DD, PP)                                   \
+    do {                                                 \
+        if (nh == 1) launch_fwd_tc<DD, PP, 1>(a);        \
+        else launch_fwd_tc<DD, PP, 2>(a);                \
+    } while (0)
     if (a.D == 64) {
-        if (poly <= 0) launch_fwd_tc<64, 0>(a);
-        else launch_fwd_tc<64, 3>(a);
+        if (poly <= 0) KF_FWD(64, 0);
+        else KF_FWD(64, 3);
     } else {
-        if (poly <= 0) launch_fwd_tc<128, 0>(a);
-        else if (poly == 2) launch_fwd_tc<128, 2>(a);
-        else if (poly == 4) launch_fwd_tc<128, 4>(a);
-        else launch_fwd_tc<128, 3>(a);
+        if (poly <= 0) KF_FWD(128, 0);
+        else if (poly == 2) KF_FWD(128, 2);
+        else if (poly == 4) KF_FWD(128, 4);
+        else KF_FWD(128, 3);
     }
+#undef KF_FWD
     return true;
 }
 

@@ -70,29 +70,38 @@ def average_gradients_(grads, dist) -> None:
 
 
 def all_reduce_grads(params, world: int, dist) -> None:
-    """sum-all-reduce every parameter gradient over the data-parallel group, then scale by 1/world."""
+    """average every parameter gradient over the data-parallel group: one NCCL all-reduce per parameter with the AVG
+    reduction (the 1/world scale happens inside the collective, no extra pass over the gradients), issued back to back on
+    the library stream so they queue behind the backward kernels that produced them."""
     import torch
 
     if world == 1:
         return
+    avg = dist.ReduceOp.AVG if dist.get_backend() == "nccl" else None
     with torch.cuda.stream(library_stream()):
         for p in params.values():
             g = p.grad()
             if not g.defined():
                 continue
             tg = as_torch(g)
-            dist.all_reduce(tg)
-            g *= 1.0 / world
+            if avg is not None:
+                dist.all_reduce(tg, op=avg)
+            else:  # gloo has no AVG
+                dist.all_reduce(tg)
+                g *= 1.0 / world
 
 
 def all_reduce_mean_scalar(t, world: int, dist):
-    """cross-shard mean of per-shard means with equal shard sizes: all-reduce(sum) / world"""
+    """cross-shard mean of per-shard means with equal shard sizes: all-reduce(AVG)"""
     import torch
 
     if world == 1:
         return t
     f = t.float()
     with torch.cuda.stream(library_stream()):
-        dist.all_reduce(as_torch(f))
-    f *= 1.0 / world
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(as_torch(f), op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(as_torch(f))
+            f *= 1.0 / world
     return f

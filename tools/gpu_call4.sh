@@ -1,6 +1,10 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-tag=s8d
-timeout 300 python -m pytest tests/test_parity_gpu.py -m gpu -x -q -k "reduce" 2>&1 | tail -4
-timeout 300 python tools/gpu_tune_reduce.py --quick 2>&1 | tee gpurun_out/${tag}_tune_reduce.log
+tag=s8f
+timeout 600 python -m pytest tests/test_attention_gpu.py -m gpu -x -q 2>&1 | tail -4
+for cfg in "2 0" "2 3" "2 2" "1 0" "1 3"; do
+  set -- $cfg
+  echo "SPLIT=$1 POLY=$2"
+  KF_ATTN_SPLIT=$1 KF_ATTN_POLY=$2 timeout 120 python tools/gpu_attn.py 2>&1 | tail -1
+done | tee gpurun_out/${tag}_attn_split.log

@@ -235,9 +235,18 @@ def time_block(kf, Event, dist, rank, world, steps, warmup, global_batch=8, S=40
     rng = np.random.default_rng(100 + rank)
     x = kf.from_numpy(rng.uniform(-1, 1, (max(bl, 1), S, E)).astype(np.float32), local).to(kf.bfloat16)
 
+    overlap = os.environ.get("KF_DP_OVERLAP", "0") == "1" and world > 1
+    if overlap:
+        from kfunca_b200.dist import OverlappedGradAllReduce
+        ar = OverlappedGradAllReduce(blk.params, world, dist)
+
     def step():
-        loss = blk.step(x)
-        all_reduce_grads(blk.params, world, dist)
+        if overlap:  # all-reduce of each gradient starts under the rest of the backward pass
+            with ar:
+                loss = blk.step(x)
+        else:
+            loss = blk.step(x)
+            all_reduce_grads(blk.params, world, dist)
         return all_reduce_mean_scalar(loss, world, dist)
 
     for _ in range(max(warmup, 3)):
@@ -247,13 +256,19 @@ def time_block(kf, Event, dist, rank, world, steps, warmup, global_batch=8, S=40
     l0 = kf.launch_count()
     marks = [Event() for _ in range(steps + 1)]  # one event per step boundary: the total is what is reported, the per-step
     marks[0].record()                            # spread (min / max) shows power-cap drift or a one-off stall
+    mallocs0 = kf.mem_stats()[2]
+    host_ms = []
     for i in range(steps):
+        t0 = time.perf_counter()
         loss = step()
         marks[i + 1].record()
+        host_ms.append((time.perf_counter() - t0) * 1e3)
     marks[-1].synchronize()
     barrier(dist)
     launches = (kf.launch_count() - l0) // steps
     per_step = [marks[i].elapsed_ms(marks[i + 1]) for i in range(steps)]
+    print(f"[block rank {rank}] per-step device ms {[round(v, 2) for v in per_step]} host-issue ms {[round(v, 2) for v in host_ms]} "
+          f"pool arena mallocs during timing {kf.mem_stats()[2] - mallocs0}", file=sys.stderr)
     ms = max_over_ranks(marks[0].elapsed_ms(marks[-1]), dist) / steps
     flops = blk.flops_per_sample(S) * global_batch
     lossv = float(loss.float().numpy().reshape(-1)[0])
@@ -261,7 +276,8 @@ def time_block(kf, Event, dist, rank, world, steps, warmup, global_batch=8, S=40
             "global_batch": global_batch, "local_batch": bl, "seq_len": S, "embed": E, "heads": H, "scaling": "strong",
             "ms_step_min": round(min(per_step), 3), "ms_step_max": round(max(per_step), 3),
             "launches_per_step": int(launches), "loss": lossv, "finite": bool(np.isfinite(lossv)),
-            "allreduce_bytes_per_step": 2 * sum(int(p.numel()) for p in blk.params.values()) if world > 1 else 0}
+            "allreduce_bytes_per_step": 2 * sum(int(p.numel()) for p in blk.params.values()) if world > 1 else 0,
+            "allreduce_overlap": bool(overlap)}
 
 
 def run_block(args):

@@ -175,6 +175,12 @@ int kf_set_requires_grad(kf_tensor_t self, int flag);
 int kf_backward(kf_tensor_t self, kf_tensor_t grad_output);
 int kf_grad(kf_tensor_t self, kf_tensor_t *out); /* *out == NULL when no grad has been accumulated */
 int kf_zero_grad(kf_tensor_t self);
+/* Leaf-gradient hook (no reference counterpart: the reference has no multi-GPU path).  `fn` runs on the calling
+ * thread inside kf_backward each time a leaf tensor's gradient for this pass has been enqueued on the library stream; `leaf`
+ * and `grad` are borrowed handles valid only during the call.  The data-parallel layer uses it to start the NCCL all-reduce of
+ * each gradient on a side stream while the rest of the backward pass is still running.  fn == NULL removes the hook. */
+typedef void (*kf_leaf_grad_hook_t)(kf_tensor_t leaf, kf_tensor_t grad, void *ctx);
+int kf_set_leaf_grad_hook(kf_leaf_grad_hook_t fn, void *ctx);
 
 /* ---- host-logic probes (no GPU needed; used by the `-m "not gpu"` tests) ------------------- */
 /* broadcast + dtype promotion + dimension collapse of `a op b` exactly as the engine plans it.

@@ -529,6 +529,20 @@ int kf_zero_grad(kf_tensor_t self) {
     T(self).impl->grad.reset();
     KF_API_END
 }
+static kf_leaf_grad_hook_t g_hook_fn = nullptr;
+static void *g_hook_ctx = nullptr;
+static void leaf_hook_trampoline(const Tensor &leaf, const Tensor &grad, void *) {
+    if (!g_hook_fn) return;
+    kf_tensor_s l{leaf}, g{grad};  // borrowed handles living on this frame
+    g_hook_fn(&l, &g, g_hook_ctx);
+}
+int kf_set_leaf_grad_hook(kf_leaf_grad_hook_t fn, void *ctx) {
+    KF_API_BEGIN
+    g_hook_fn = fn;
+    g_hook_ctx = ctx;
+    ops::set_leaf_grad_hook(fn ? leaf_hook_trampoline : nullptr, nullptr);
+    KF_API_END
+}
 
 // ---------------------------------------------------------------- host-logic probes
 int kf_debug_plan_binary(kf_tensor_t a, kf_tensor_t b, int *ndim, int64_t *shape, int64_t *strides3, int *common_dtype) {

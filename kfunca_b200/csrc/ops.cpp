@@ -815,6 +815,13 @@ std::tuple<Tensor, Tensor, Tensor> causal_attention_bwd(const Tensor &dout_, con
 // ================================================================== autograd engine
 // Same two-pass scheme as the reference (src/core/tensor.cpp:86-126): count consumers, then a ready
 // queue; leaf grads accumulate across backward() calls (tensor.cpp:75-84).
+static LeafGradHook g_leaf_hook = nullptr;
+static void *g_leaf_hook_ctx = nullptr;
+void set_leaf_grad_hook(LeafGradHook fn, void *ctx) {
+    g_leaf_hook = fn;
+    g_leaf_hook_ctx = ctx;
+}
+
 void backward(Tensor &root, const Tensor &grad_output) {
     KF_CHECK(root.defined() && grad_output.defined());
     std::unordered_map<TensorImpl *, int> needed;
@@ -861,6 +868,7 @@ void backward(Tensor &root, const Tensor &grad_output) {
                 run_copy(gcopy, go);
                 impl->grad.reset(new Tensor(gcopy));
             }
+            if (g_leaf_hook) g_leaf_hook(*t, *impl->grad, g_leaf_hook_ctx);
         }
     }
 }

@@ -61,6 +61,11 @@ std::tuple<Tensor, Tensor, Tensor> causal_attention_bwd(const Tensor &dout, cons
 
 // ---- autograd (ref: Tensor::backward, src/core/tensor.cpp:86-126)
 void backward(Tensor &root, const Tensor &grad_output);
+// Called (on the calling thread, inside backward()) right after a leaf's gradient for this pass has been enqueued: the hook may
+// order other streams behind the library stream and start the data-parallel all-reduce of that gradient while the rest of the
+// backward pass is still being issued.  Not in the reference (it has no multi-GPU path); nullptr disables it.
+using LeafGradHook = void (*)(const Tensor &leaf, const Tensor &grad, void *ctx);
+void set_leaf_grad_hook(LeafGradHook fn, void *ctx);
 
 }  // namespace ops
 }  // namespace kf

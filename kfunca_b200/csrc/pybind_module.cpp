@@ -207,6 +207,29 @@ PYBIND11_MODULE(_kfunca, m) {
     m.def("set_device", [](int d) { ck(kf_set_device(d)); });
     m.def("device_count", []() { int n; ck(kf_device_count(&n)); return n; });
     m.def("launch_count", []() { int64_t n; ck(kf_launch_count(&n)); return n; });
+    // set_leaf_grad_hook(fn | None): fn(leaf, grad) is called inside backward() as each leaf gradient is enqueued (see the header)
+    m.def("set_leaf_grad_hook", [](py::object fn) {
+        static py::object *held = new py::object();  // leaked on purpose: must outlive interpreter finalisation order
+        if (fn.is_none()) {
+            ck(kf_set_leaf_grad_hook(nullptr, nullptr));
+            *held = py::none();
+            return;
+        }
+        *held = fn;
+        ck(kf_set_leaf_grad_hook(
+            [](kf_tensor_t leaf, kf_tensor_t grad, void *ctx) {
+                py::gil_scoped_acquire gil;
+                kf_tensor_t l2 = nullptr, g2 = nullptr;  // owning handles for Python
+                if (kf_retain(leaf, &l2) != 0 || kf_retain(grad, &g2) != 0) return;
+                try {
+                    (*static_cast<py::object *>(ctx))(PyTensor(l2), PyTensor(g2));
+                } catch (py::error_already_set &e) {  // a Python error must not unwind through the C ABI
+                    e.restore();
+                    PyErr_Print();
+                }
+            },
+            held));
+    });
     m.def("stream", []() { void *s; ck(kf_stream(&s)); return (uintptr_t)s; });
 
     py::enum_<kf_dtype_t>(m, "dtype")

@@ -105,3 +105,56 @@ def all_reduce_mean_scalar(t, world: int, dist):
             dist.all_reduce(as_torch(f))
             f *= 1.0 / world
     return f
+
+
+class OverlappedGradAllReduce:
+    """Start the all-reduce (AVG) of every parameter gradient the moment the backward pass has enqueued it, on a side stream, so
+    NCCL over NVLink runs under the rest of the backward pass instead of after it.
+
+        with OverlappedGradAllReduce(params, world, dist):
+            loss = block.step(x)          # backward() fires the leaf-gradient hook once per parameter
+        # on exit the library stream waits for the side stream: gradients are averaged for whoever reads them next
+
+    Mechanics: the hook (kf.set_leaf_grad_hook) records an event on the library stream, the side stream waits for it and the
+    collective is issued there.  Gradient memory is owned by the parameter until the next zero_grad(), which is ordered after
+    the join, so the pool's single-stream free rule still holds."""
+
+    def __init__(self, params, world: int, dist):
+        import torch
+
+        self.world, self.dist, self.torch = world, dist, torch
+        self.ptrs = {p.data_ptr() for p in params.values()}
+        self.active = world > 1
+        if self.active:
+            self.lib = library_stream()
+            self.side = torch.cuda.Stream()
+            self.avg = dist.ReduceOp.AVG if dist.get_backend() == "nccl" else None
+        self.count = 0
+
+    def _hook(self, leaf, grad):
+        if leaf.data_ptr() not in self.ptrs:
+            return
+        torch = self.torch
+        ev = torch.cuda.Event()
+        ev.record(self.lib)
+        self.side.wait_event(ev)
+        with torch.cuda.stream(self.side):
+            tg = as_torch(grad)
+            if self.avg is not None:
+                self.dist.all_reduce(tg, op=self.avg)
+            else:
+                self.dist.all_reduce(tg)
+                tg.mul_(1.0 / self.world)
+        self.count += 1
+
+    def __enter__(self):
+        if self.active:
+            self.count = 0
+            kf.set_leaf_grad_hook(self._hook)
+        return self
+
+    def __exit__(self, *exc):
+        if self.active:
+            kf.set_leaf_grad_hook(None)
+            self.lib.wait_stream(self.side)
+        return False

@@ -63,3 +63,25 @@ def test_block_forward_backward_matches_torch_autograd(dtype, B, S, E, H, tol):
         assert np.abs(got - exp).max() <= tol * scale, (n, np.abs(got - exp).max(), scale)
     got, exp = host(x.grad()), tx.grad.numpy()
     assert np.abs(got - exp).max() <= tol * np.abs(exp).max()
+
+
+def test_leaf_grad_hook_fires_once_per_parameter_with_the_final_gradient():
+    """kf.set_leaf_grad_hook (the data-parallel overlap entry point): called inside backward(), once per leaf, with the
+    gradient tensor that p.grad() returns afterwards (same storage)."""
+    blk = Block(128, 2, dtype=kf.float, device=0, seed=1)
+    x = kf.from_numpy(np.random.default_rng(2).uniform(-1, 1, (2, 64, 128)).astype(np.float32), 0)
+    seen = []
+    kf.set_leaf_grad_hook(lambda leaf, grad: seen.append((leaf.data_ptr(), grad.data_ptr(), tuple(grad.sizes()))))
+    try:
+        blk.step(x)
+    finally:
+        kf.set_leaf_grad_hook(None)
+    kf.synchronize()
+    by_leaf = {l: (g, s) for l, g, s in seen}
+    assert len(seen) == len(blk.params) == len(by_leaf)
+    for n, p in blk.params.items():
+        g, s = by_leaf[p.data_ptr()]
+        assert g == p.grad().data_ptr() and s == tuple(p.sizes()), n
+    seen.clear()
+    blk.step(x)  # hook removed: nothing recorded
+    assert not seen

@@ -164,6 +164,29 @@ def test_pool_allocator_reuse_split_coalesce():
     assert reserved == 2 * MiB and in_use == 1024
 
 
+def test_pool_grows_in_slabs_once_it_is_large():
+    """>= 1 GiB reserved: a miss reserves a quarter of the pool (not the exact request), so a repeating allocation pattern
+    stops calling the driver (steady state of a training step)."""
+    MiB = 1 << 20
+    big = 64 * MiB
+    offs, (in_use, reserved, mallocs) = kf.debug_pool_trace([big] * 16)
+    assert mallocs == 16 and reserved == 16 * big  # below 1 GiB: exact-size arenas
+    offs, (in_use, reserved, mallocs) = kf.debug_pool_trace([big] * 17)
+    assert mallocs == 17 and reserved == 16 * big + 256 * MiB  # the 17th miss takes 1024 / 4 MiB
+    offs, (in_use, reserved, mallocs) = kf.debug_pool_trace([big] * 20)
+    assert mallocs == 17 and in_use == 20 * big  # ... which serves the next three requests without the driver
+    # a repeating "step" (allocate a mixed set, free it all) settles: the second and third pass add no driver calls
+    step = [big, 300 * MiB, 3 * MiB, big, 700 * MiB, 1000, big, 128 * MiB]
+    ops, base = [], 0
+    counts = []
+    for rep in range(3):
+        ops += step
+        ops += [-(base + i + 1) for i in range(len(step))]
+        base += 2 * len(step)
+        counts.append(kf.debug_pool_trace(ops)[1][2])
+    assert counts[1] == counts[0] == counts[2]
+
+
 def test_compute_without_gpu_fails_loudly():
     a = meta((2, 2))
     for fn in (lambda: a + a, lambda: a.sum(0), lambda: a.contiguous() if False else a.permute(1, 0).contiguous(),

@@ -235,7 +235,7 @@ def time_block(kf, Event, dist, rank, world, steps, warmup, global_batch=8, S=40
     rng = np.random.default_rng(100 + rank)
     x = kf.from_numpy(rng.uniform(-1, 1, (max(bl, 1), S, E)).astype(np.float32), local).to(kf.bfloat16)
 
-    overlap = os.environ.get("KF_DP_OVERLAP", "0") == "1" and world > 1
+    overlap = os.environ.get("KF_DP_OVERLAP", "1") == "1" and world > 1  # default on; KF_DP_OVERLAP=0 = all-reduce after backward
     if overlap:
         from kfunca_b200.dist import OverlappedGradAllReduce
         ar = OverlappedGradAllReduce(blk.params, world, dist)

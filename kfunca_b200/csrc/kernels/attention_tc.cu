@@ -95,13 +95,14 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
 // threads per row (warps w and w + 4 of the tile own columns [0, 64) and [64, 128)), so every dependent step (TMEM load, max
 // tree, exp, TMEM store) is half as long.  The halves agree on the row maximum through shared memory and one 64-thread named
 // barrier per block; that barrier also orders "both halves have loaded S" before either overwrites S with P.
-// S row from tensor memory, [mask], row max, lazy rescale of O / l, P = exp2(S c - m) written back over S as 16-bit, running
+// S row from tensor memory, [mask], row max, lazy rescale of O / l, P = exp2(S c - m) written back over S as 16-bit (each 64-key
+// half is signalled on its own mbarrier `p_half[..]` as soon as it is stored), running
 // row sum (per half).  `lim`: columns > lim (relative to this half) are masked.  POLY: of every 8 column pairs, this many take
 // the FMA-pipe exp2.
 template <int D, bool BF16, bool MASKED, int POLY, int NH>
 __device__ __forceinline__ void fwd_softmax_block(const uint32_t s_addr, const uint32_t p_addr, const uint32_t o_addr, const float sc, const int lim,
                                                   const bool first, float &m_ref, float &l_run, float *xch_mine, const float *xch_peer,
-                                                  const int bar_id) {
+                                                  const int bar_id, uint64_t *p_half) {
     constexpr int NC = 4 / NH;  // 32-column chunks per thread
     uint32_t s[NC][32];
 #pragma unroll
@@ -169,6 +170,11 @@ __device__ __forceinline__ void fwd_softmax_block(const uint32_t s_addr, const u
                 pk[h * 16 + (i >> 1)] = pack16t<BF16>(x);
             }
         tmem_st32(p_addr + (uint32_t)(c * 16), pk);
+        // hand this 64-key half of P to the MMA warp right away: the first four k-steps of P V run under the second half's exps
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(p_half + (NH == 1 ? c / 2 : 0));
     }
     l_run += (rs2.x + rs2.y) + (rs3.x + rs3.y);
 }
@@ -205,8 +211,8 @@ __device__ __forceinline__ void attn_fwd_tc_body(const CUtensorMap &tmap_q, cons
     uint64_t *q_full = bars + 0;
     uint64_t *kv_full = bars + 1, *kv_empty = bars + 1 + NS;
     uint64_t *s_full = bars + 1 + 2 * NS;  // [2]
-    uint64_t *p_full = s_full + 2;         // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(p_full + 2);
+    uint64_t *p_full = s_full + 2;         // [2 tiles][2 key halves]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(p_full + 4);
     float *xch = reinterpret_cast<float *>(smem + (2 + NS) * TILE_BYTES + 256);  // [tile][half][parity][row] row-max / row-sum exchange (NH = 2)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -232,7 +238,8 @@ __device__ __forceinline__ void attn_fwd_tc_body(const CUtensorMap &tmap_q, cons
         }
         for (int t = 0; t < 2; ++t) {
             mbar_init(&s_full[t], 1);
-            mbar_init(&p_full[t], 4 * NH);
+            mbar_init(&p_full[2 * t], 4);
+            mbar_init(&p_full[2 * t + 1], 4);
         }
         fence_barrier_init();
     }
@@ -286,9 +293,9 @@ __device__ __forceinline__ void attn_fwd_tc_body(const CUtensorMap &tmap_q, cons
                                make_sw128_desc(k_addr + off, 0, 1024), idesc_s, kk ? 1u : 0u, leader);
                 }
             };
-            auto issue_pv = [&](int t, uint32_t v_addr, bool accumulate) {
+            auto issue_pv = [&](int t, uint32_t v_addr, bool accumulate, int half) {
 #pragma unroll
-                for (int kk = 0; kk < FA_BKV / 16; ++kk) {
+                for (int kk = half * (FA_BKV / 32); kk < (half + 1) * (FA_BKV / 32); ++kk) {
                     // A = P from tensor memory: 16 k-values of 16 bits = 8 columns per step;
                     // B = V, MN-major: 16 kv rows = 2 x 1024 B per step, 64-wide d atoms ATOM_BYTES apart
                     umma_f16_ts_p(tmem_base + O_COL + (uint32_t)(t * D), tmem_base + (uint32_t)(t * 128 + kk * 8),
@@ -326,9 +333,12 @@ __device__ __forceinline__ void attn_fwd_tc_body(const CUtensorMap &tmap_q, cons
                 for (int t = 0; t < 2; ++t) {
                     const int nb_t = t ? nblk1 : nblk0;
                     if (j - 1 < nb_t) {
-                        mbar_wait(&p_full[t], (uint32_t)((j - 1) & 1));
+                        mbar_wait(&p_full[2 * t], (uint32_t)((j - 1) & 1));
                         tc_fence_after();
-                        issue_pv(t, kv_addr + sv * TILE_BYTES, j > 1);
+                        issue_pv(t, kv_addr + sv * TILE_BYTES, j > 1, 0);
+                        mbar_wait(&p_full[2 * t + 1], (uint32_t)((j - 1) & 1));
+                        tc_fence_after();
+                        issue_pv(t, kv_addr + sv * TILE_BYTES, true, 1);
                         if (j < nb_t) issue_s(t, kv_addr + sk * TILE_BYTES);
                         umma_commit_p(&s_full[t], leader);
                     }
@@ -366,19 +376,16 @@ __device__ __forceinline__ void attn_fwd_tc_body(const CUtensorMap &tmap_q, cons
                 const bool masked = (kv0 + FA_BKV - 1 > q0t) || (kv0 + FA_BKV > p.Skv);  // diagonal / ragged block (CTA-uniform per tile)
                 const int64_t lim64 = min(m_row, p.Skv - 1) - kv0 - h * HC;             // columns i > lim (of this half) are masked
                 const int lim = (int)max((int64_t)-1, min(lim64, (int64_t)127));
+                uint64_t *p_bar = &p_full[2 * t + h];  // NH = 1: halves 0 and 1 in turn; NH = 2: this warp's half
                 float *xm_j = xm + (j & 1) * 128;
                 const float *xp_j = xp + (j & 1) * 128;
                 if (p.is_bf16) {
-                    if (masked) fwd_softmax_block<D, true, true, POLY, NH>(s_addr, p_addr, o_addr, sc, lim, j == 0, m_ref, l_run, xm_j, xp_j, bar_id);
-                    else fwd_softmax_block<D, true, false, POLY, NH>(s_addr, p_addr, o_addr, sc, lim, j == 0, m_ref, l_run, xm_j, xp_j, bar_id);
+                    if (masked) fwd_softmax_block<D, true, true, POLY, NH>(s_addr, p_addr, o_addr, sc, lim, j == 0, m_ref, l_run, xm_j, xp_j, bar_id, p_bar);
+                    else fwd_softmax_block<D, true, false, POLY, NH>(s_addr, p_addr, o_addr, sc, lim, j == 0, m_ref, l_run, xm_j, xp_j, bar_id, p_bar);
                 } else {
-                    if (masked) fwd_softmax_block<D, false, true, POLY, NH>(s_addr, p_addr, o_addr, sc, lim, j == 0, m_ref, l_run, xm_j, xp_j, bar_id);
-                    else fwd_softmax_block<D, false, false, POLY, NH>(s_addr, p_addr, o_addr, sc, lim, j == 0, m_ref, l_run, xm_j, xp_j, bar_id);
+                    if (masked) fwd_softmax_block<D, false, true, POLY, NH>(s_addr, p_addr, o_addr, sc, lim, j == 0, m_ref, l_run, xm_j, xp_j, bar_id, p_bar);
+                    else fwd_softmax_block<D, false, false, POLY, NH>(s_addr, p_addr, o_addr, sc, lim, j == 0, m_ref, l_run, xm_j, xp_j, bar_id, p_bar);
                 }
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&p_full[t]);
             }
             // ---- epilogue: O / l -> 16-bit -> global, row LSE
             if (NH == 2) {  // total row sum = sum of the two halves (slot parity n_t: the last block used parity (n_t - 1) & 1)
@@ -469,8 +476,9 @@ bool launch_attention_fwd_tc(const AttnPlan &a) {
     if (a.Sq < 1 || a.Skv < 1 || a.BH < 1 || a.BH >= 65536) return false;
     auto al = [](const void *p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
     if (!al(a.q) || !al(a.k) || !al(a.v) || !al(a.out)) return false;
-    // share of the exponentials computed on the FMA pipe instead of the MUFU unit (tuning hook; default 0: measured slower at 2..4 of 8 while MMA issue, not MUFU, was the limiter)
-    static const int poly = std::getenv("KF_ATTN_POLY") ? std::atoi(std::getenv("KF_ATTN_POLY")) : 0;
+    // share of the exponentials computed on the FMA pipe instead of the MUFU unit, in eighths (KF_ATTN_POLY; measured at C3:
+    // 0 -> 1066, 2 -> 1082, 3 -> 1064 TFLOP/s with the split P hand-off; default 2)
+    static const int poly = std::getenv("KF_ATTN_POLY") ? std::atoi(std::getenv("KF_ATTN_POLY")) : 2;
     // threads per query row in the softmax (see fwd_softmax_block).  Measured at C3: one thread per row 1.08 ms (1017 TFLOP/s), two
     // threads per row 1.34 ms (818 TFLOP/s) — the extra named barrier, doubled polling and 96-register budget cost more than the
     // shorter dependent chains gain, so KF_ATTN_SPLIT=2 stays an opt-in experiment

@@ -309,7 +309,9 @@ def load_traffic(kernel):
     """dram bytes per launch from the committed ncu capture (profiles/traffic.json), or null"""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(path):
-        return json.load(open(path)).get(kernel)
+        for k, v in json.load(open(path)).items():
+            if k.split()[-1] == kernel:  # ncu names read "void gemm_tc2_kernel"
+                return v
     return None
 
 

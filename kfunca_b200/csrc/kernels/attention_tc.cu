@@ -7,7 +7,10 @@
 //   warp 8    : MMA issuer   S_t = Q_t K_j^T  (128x128xD, both operands K-major in smem, fp32 accumulator in TMEM)
 //                            O_t += P_t V_j   (128xDx128, P read from TENSOR MEMORY, V MN-major in smem)
 //               issue order  S_0, S_1, then per block { P_0 V + next S_0 ; P_1 V + next S_1 } so the tensor pipe works on
-//               one tile while the softmax warps of the other tile run (ping-pong).
+//               one tile while the softmax warps of the other tile run (ping-pong).  P_t is handed over in two 64-key halves, so
+//               the first four k-steps of P V run under the second half's exponentials.
+//               (Tried and rejected, 1082 -> 811 TFLOP/s: issuing the upper 64 columns of the next S early as an N = 64 MMA.
+//               An M128 N64 K16 MMA still reads the whole 4 KB A slice from shared memory, so two of them cost 1.5x one N = 128.)
 //   warps 0-3 / 4-7 : softmax of tile 0 / 1.  thread = query row: one tcgen05.ld of the whole S row (128 fp32 registers),
 //               max, exp2 in packed fp32x2 FMAs, P (16-bit) written back over S in TMEM (tcgen05.st).  The running max is
 //               LAZY: it only moves (and O, l are only rescaled) when the row max grew by more than 2^8, which is exact

@@ -211,7 +211,7 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
                      "traffic": load_traffic("gemm_tc2_kernel"), "peak_kind": "burst bf16 cuBLAS, " + peaks["source"],
-                     "kernel": "gemm_tc2_kernel<256,false,false> (CTA pair, cta_group::2)"},
+                     "kernel": "gemm_tc2_kernel<256,false,true> (CTA pair, cta_group::2; B is [K,N] row-major = N-major operand)"},
     }
     out["cpu_baseline"] = cpu_baseline_gemm(a_host.array.view(O.bfloat16), b_host.array.view(O.bfloat16))
     if not args.no_extras and world == 1:
@@ -258,8 +258,10 @@ def time_block(kf, Event, dist, rank, world, steps, warmup, global_batch=8, S=40
     marks[0].record()                            # spread (min / max) shows power-cap drift or a one-off stall
     mallocs0 = kf.mem_stats()[2]
     host_ms = []
+    loss = None
     for i in range(steps):
         t0 = time.perf_counter()
+        loss = None  # drop the previous step's autograd graph (and its saved activations) before building the next one
         loss = step()
         marks[i + 1].record()
         host_ms.append((time.perf_counter() - t0) * 1e3)

@@ -366,7 +366,20 @@ def extras(kf, Event, peaks):
     mem("c1_mean_dim0", lambda i: A[i].mean(0), nb + N * 4)
     mem("c1_mean_dim1", lambda i: A[i].mean(1), nb + N * 4)
     mem("c1_permute_contiguous", lambda i: A[i].permute(1, 0).contiguous(), 2 * nb)
-    del A, B
+    # fused layer norm over rows of 4096 (the block's shape class), fp32: forward reads x + writes y,
+    # backward reads x, dy + writes dx (statistics and the gain gradient are < 0.1 % of the bytes)
+    gain = kf.from_numpy(rng.uniform(0.5, 1.5, (1, N)).astype(np.float32), 0)
+    mem("f1_layer_norm_fwd_fp32_4096", lambda i: kf.layer_norm(A[i], gain, 1e-5), 2 * nb)
+    for a_ in A:
+        a_.set_requires_grad(True)
+    ys = [kf.layer_norm(A[i], gain, 1e-5) for i in range(nsets)]
+
+    def ln_bwd(i):
+        A[i].zero_grad()
+        ys[i].backward(B[i])
+
+    mem("f1_layer_norm_bwd_fp32_4096", ln_bwd, 3 * nb)
+    del A, B, ys
     # C4 top-k at reduced row count (8192 x 32768 fp32 = 1 GiB > L2; full 65536 rows is the same kernel, 8x longer)
     rows, cols, k = 8192, 32768, 64
     X = kf.from_numpy(rng.uniform(-1e5, 1e5, (rows, cols)).astype(np.float32), 0)

@@ -169,6 +169,12 @@ int kf_causal_attention_fwd(kf_tensor_t q, kf_tensor_t k, kf_tensor_t v, kf_tens
 int kf_causal_attention_bwd(kf_tensor_t dout, kf_tensor_t q, kf_tensor_t k, kf_tensor_t v, kf_tensor_t out,
                             kf_tensor_t lse, kf_tensor_t *dq, kf_tensor_t *dk, kf_tensor_t *dv);
 
+/* Fused layer norm over the last dimension: y = (x - mean) / sqrt(var + eps) * gain, biased variance, gain has size(-1)
+ * elements; differentiable in x and gain.  The reference stops at the statistics (mean_var, norm_stat:
+ * src/device/reduce_ops_kernel.cu:61-153, src/device/norm_ops_kernel.cu:6-61) and lists the fused norm as its next op
+ * (README.md:28); SURVEY §8f rank 1. */
+int kf_layer_norm(kf_tensor_t x, kf_tensor_t gain, double eps, kf_tensor_t *out);
+
 /* ---- autograd (ref: GradFunction/backward, tensor.h:18-22, tensor.cpp:71-126) -------------- */
 int kf_requires_grad(kf_tensor_t self, int *out);
 int kf_set_requires_grad(kf_tensor_t self, int flag);

@@ -2,6 +2,7 @@
 (gemm, causal_attention, + - * /, mean, permute/view/split/contiguous) so it is expressible through the
 reference's register.cpp names; forward + backward through the library's autograd.
 
+  (the two layer norms default to the fused kf.layer_norm kernel pair; fused_norm=False composes them from mean / - / * / rsqrt)
   x:[B,S,E] -> LN1 -> qkv = gemm(xn, Wqkv[E,3E]) -> split -> [B,H,S,D] -> causal_attention -> [B,S,E]
     -> x1 = x + gemm(o, Wo) -> LN2 -> h = gemm(xn2, W1) * gemm(xn2, W3) -> y = x1 + gemm(h, W2[4E,E]); loss = mean(y)
 """
@@ -13,15 +14,22 @@ import kfunca_b200 as kf
 
 
 def _norm(x, gain, eps=1e-5):
+    """layer norm composed from the reference's own operator set (mean, - , *, rsqrt): 8 launches forward"""
     mu = x.mean(-1)
     xc = x - mu
     var = (xc * xc).mean(-1)
     return xc * kf.rsqrt(var + eps) * gain
 
 
+def _norm_fused(x, gain, eps=1e-5):
+    """the same function as ONE kernel forward and one backward (kf.layer_norm)"""
+    return kf.layer_norm(x, gain, eps)
+
+
 class Block:
-    def __init__(self, E: int, H: int, dtype=None, device: int = 0, seed: int = 0, ffn_mult: int = 4):
+    def __init__(self, E: int, H: int, dtype=None, device: int = 0, seed: int = 0, ffn_mult: int = 4, fused_norm: bool = True):
         assert E % H == 0
+        self.norm = _norm_fused if fused_norm else _norm
         self.E, self.H, self.D, self.F = E, H, E // H, ffn_mult * E
         self.dtype = dtype or kf.bfloat16
         rng = np.random.default_rng(seed)
@@ -44,14 +52,14 @@ class Block:
         p = self.params
         B, S, E = x.sizes()
         H, D = self.H, self.D
-        xn = _norm(x, p["g1"])
+        xn = self.norm(x, p["g1"])
         qkv = kf.gemm(xn, p["wqkv"], 1.0, 0.0)
         q, k, v = qkv.split([E, E, E], -1)
         heads = lambda t: t.contiguous().view(B, S, H, D).permute(0, 2, 1, 3).contiguous()
         o = kf.causal_attention(heads(q), heads(k), heads(v))
         o = o.permute(0, 2, 1, 3).contiguous().view(B, S, E)
         x1 = x + kf.gemm(o, p["wo"], 1.0, 0.0)
-        xn2 = _norm(x1, p["g2"])
+        xn2 = self.norm(x1, p["g2"])
         h = kf.gemm(xn2, p["w1"], 1.0, 0.0) * kf.gemm(xn2, p["w3"], 1.0, 0.0)
         return x1 + kf.gemm(h, p["w2"], 1.0, 0.0)
 

@@ -502,6 +502,11 @@ int kf_causal_attention_bwd(kf_tensor_t dout, kf_tensor_t q, kf_tensor_t k, kf_t
     KF_API_END
 }
 
+int kf_layer_norm(kf_tensor_t x, kf_tensor_t gain, double eps, kf_tensor_t *out) {
+    KF_API_BEGIN
+    *out = wrap(ops::layer_norm(T(x), T(gain), eps));
+    KF_API_END
+}
 // ---------------------------------------------------------------- autograd
 int kf_requires_grad(kf_tensor_t self, int *out) {
     KF_API_BEGIN

@@ -106,6 +106,14 @@ bool launch_attention_bwd_tc(const AttnBwdPlan &p);  // false => caller uses the
 // P = exp(S - lse) under the causal mask, in place, fp32 / fp64 (generic backward helper)
 void launch_attn_probs(void *S, const void *lse, int dtype, int64_t BH, int64_t Sq, int64_t Skv);
 
+// Fused layer normalisation over the last dimension (kernels/norm.cu): y = (x - mean) * rstd * gain with biased variance.
+// `layer_norm_supported` is false for dtypes / row lengths the register-resident kernels do not cover (caller composes the op).
+bool layer_norm_supported(int dtype, int64_t E, const void *x, const void *gain);
+void launch_layer_norm_fwd(const void *x, const void *gain, void *y, float *mean, float *rstd, int dtype, int64_t rows, int64_t E, float eps);
+int layer_norm_bwd_ctas(int64_t rows);
+void launch_layer_norm_bwd(const void *x, const void *gain, const void *dy, const float *mean, const float *rstd, void *dx,
+                           float *dgain_partial, int ctas, int dtype, int64_t rows, int64_t E);
+
 std::string device_info_string();
 
 // host-side 16-bit float helpers (RN-even, NaN-preserving), ref: src/core/include/half.h:195-208,268-290

@@ -1,0 +1,259 @@
+// Fused layer normalisation over the last dimension, forward and backward (the reference stops at the
+// statistics — `mean_var` / `norm_stat`, src/device/reduce_ops_kernel.cu:61-153, src/device/norm_ops_kernel.cu:6-61,
+// src/device/utils/welford_norm.h:25-355 — and lists the fused norm as the next unchecked op, README.md:28).
+//
+//   y = (x - mean) * rstd * gain,   mean = E[x],  rstd = 1 / sqrt(E[(x - mean)^2] + eps)        (biased variance, per row)
+//
+// HBM-bound: forward reads x once and writes y once (+ 8 B of statistics per row); backward reads x and dy once, writes dx
+// once.  The composed form the transformer block used before (mean, sub, mul, mean, add, rsqrt, mul, mul) moves ~10x the bytes
+// forward and ~25x backward.
+//
+// One row is held in registers by 128 threads (NV 16-byte vectors each), so the statistics are the exact two-pass ones
+// (mean first, then the centred second moment) at single-read cost — no Welford merge and no E[x^2] - E[x]^2 cancellation.
+//   forward : one row per CTA.
+//   backward: persistent CTAs stride over the rows; each thread keeps the gain-gradient partial sums of ITS columns in
+//             registers across rows, writes them once to a [CTAs, E] fp32 scratch, and the ordinary column reduction folds
+//             that scratch afterwards: deterministic, no atomics.
+#include "ew_common.cuh"
+
+namespace kf {
+
+constexpr int LN_THREADS = 128;
+
+__device__ __forceinline__ float ln_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// sum over the 128 threads of the CTA, result in every thread; `slot` = 4 floats of shared memory not in use by another sum
+__device__ __forceinline__ float ln_block_sum(float v, float *slot) {
+    v = ln_warp_sum(v);
+    if ((threadIdx.x & 31) == 0) slot[threadIdx.x >> 5] = v;
+    __syncthreads();
+    return (slot[0] + slot[1]) + (slot[2] + slot[3]);
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ Pack<T, VEC> ln_ld(const T *p) {
+    return *reinterpret_cast<const Pack<T, VEC> *>(p);
+}
+
+struct LnArgs {
+    const void *x, *gain, *dy;
+    void *y, *dx;
+    float *mean, *rstd;      // [rows]
+    float *dgain_partial;    // [gridDim.x, E] (backward)
+    int64_t rows, E;
+    float eps;
+};
+
+template <typename T, int VEC, int NV>
+__global__ void __launch_bounds__(LN_THREADS) layer_norm_fwd_kernel(const LnArgs a) {
+    __shared__ float red[8];
+    const int64_t row = blockIdx.x;
+    const int nvec = (int)(a.E / VEC);
+    const T *__restrict__ x = reinterpret_cast<const T *>(a.x) + row * a.E;
+    float v[NV][VEC];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int iv = threadIdx.x + k * LN_THREADS;
+        if (iv < nvec) {
+            const Pack<T, VEC> pk = ln_ld<T, VEC>(x + (int64_t)iv * VEC);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                v[k][i] = cvt_in<float>(pk.v[i]);
+                s += v[k][i];
+            }
+        }
+    }
+    const float mean = ln_block_sum(s, red) / (float)a.E;
+    float d = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int iv = threadIdx.x + k * LN_THREADS;
+        if (iv < nvec) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                v[k][i] -= mean;
+                d += v[k][i] * v[k][i];
+            }
+        }
+    }
+    const float rstd = rsqrtf(ln_block_sum(d, red + 4) / (float)a.E + a.eps);
+    if (threadIdx.x == 0) {
+        a.mean[row] = mean;
+        a.rstd[row] = rstd;
+    }
+    const T *__restrict__ g = reinterpret_cast<const T *>(a.gain);
+    T *__restrict__ y = reinterpret_cast<T *>(a.y) + row * a.E;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int iv = threadIdx.x + k * LN_THREADS;
+        if (iv < nvec) {
+            const Pack<T, VEC> gk = ln_ld<T, VEC>(g + (int64_t)iv * VEC);
+            Pack<T, VEC> out;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) out.v[i] = cvt_out<T, float>(v[k][i] * rstd * cvt_in<float>(gk.v[i]));
+            *reinterpret_cast<Pack<T, VEC> *>(y + (int64_t)iv * VEC) = out;
+        }
+    }
+}
+
+// dx = rstd * (gg - mean_e(gg) - xhat * mean_e(gg * xhat)),  gg = dy * gain,  xhat = (x - mean) * rstd
+// dgain[e] = sum_rows dy * xhat  (per-CTA partial rows here, folded by the caller)
+template <typename T, int VEC, int NV, bool WRITE_DX>
+__global__ void __launch_bounds__(LN_THREADS) layer_norm_bwd_kernel(const LnArgs a) {
+    __shared__ float red[2][8];
+    const int nvec = (int)(a.E / VEC);
+    const T *__restrict__ gp = reinterpret_cast<const T *>(a.gain);
+    float gain[NV][VEC], dgain[NV][VEC];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int iv = threadIdx.x + k * LN_THREADS;
+        Pack<T, VEC> gk{};
+        if (iv < nvec) gk = ln_ld<T, VEC>(gp + (int64_t)iv * VEC);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            gain[k][i] = iv < nvec ? cvt_in<float>(gk.v[i]) : 0.f;
+            dgain[k][i] = 0.f;
+        }
+    }
+    int it = 0;
+    for (int64_t row = blockIdx.x; row < a.rows; row += gridDim.x, ++it) {
+        const T *__restrict__ x = reinterpret_cast<const T *>(a.x) + row * a.E;
+        const T *__restrict__ dy = reinterpret_cast<const T *>(a.dy) + row * a.E;
+        const float mean = a.mean[row], rstd = a.rstd[row];
+        float xh[NV][VEC], gg[NV][VEC];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int iv = threadIdx.x + k * LN_THREADS;
+            if (iv < nvec) {
+                const Pack<T, VEC> xk = ln_ld<T, VEC>(x + (int64_t)iv * VEC);
+                const Pack<T, VEC> dk = ln_ld<T, VEC>(dy + (int64_t)iv * VEC);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const float g = cvt_in<float>(dk.v[i]);
+                    xh[k][i] = (cvt_in<float>(xk.v[i]) - mean) * rstd;
+                    gg[k][i] = g * gain[k][i];
+                    dgain[k][i] += g * xh[k][i];
+                    s1 += gg[k][i];
+                    s2 += gg[k][i] * xh[k][i];
+                }
+            }
+        }
+        if (WRITE_DX) {
+            // both row sums in one barrier round; the shared slots alternate between iterations so the next row's writers cannot
+            // overtake this row's readers
+            float *slot = red[it & 1];
+            s1 = ln_warp_sum(s1);
+            s2 = ln_warp_sum(s2);
+            if ((threadIdx.x & 31) == 0) {
+                slot[threadIdx.x >> 5] = s1;
+                slot[4 + (threadIdx.x >> 5)] = s2;
+            }
+            __syncthreads();
+            const float c1 = ((slot[0] + slot[1]) + (slot[2] + slot[3])) / (float)a.E;
+            const float c2 = ((slot[4] + slot[5]) + (slot[6] + slot[7])) / (float)a.E;
+            T *__restrict__ dx = reinterpret_cast<T *>(a.dx) + row * a.E;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                const int iv = threadIdx.x + k * LN_THREADS;
+                if (iv < nvec) {
+                    Pack<T, VEC> out;
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) out.v[i] = cvt_out<T, float>(rstd * (gg[k][i] - c1 - xh[k][i] * c2));
+                    *reinterpret_cast<Pack<T, VEC> *>(dx + (int64_t)iv * VEC) = out;
+                }
+            }
+        }
+    }
+    float *__restrict__ part = a.dgain_partial + (int64_t)blockIdx.x * a.E;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int iv = threadIdx.x + k * LN_THREADS;
+        if (iv < nvec) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) part[(int64_t)iv * VEC + i] = dgain[k][i];
+        }
+    }
+}
+
+template <typename T>
+static int ln_nv(int64_t E) {
+    constexpr int VEC = 16 / sizeof(T);
+    const int64_t nvec = E / VEC;
+    const int64_t per = (nvec + LN_THREADS - 1) / LN_THREADS;
+    return per <= 1 ? 1 : per <= 2 ? 2 : per <= 4 ? 4 : per <= 8 ? 8 : 0;
+}
+
+bool layer_norm_supported(int dtype, int64_t E, const void *x, const void *gain) {
+    if (dtype != KF_FLOAT && dtype != KF_HALF && dtype != KF_BFLOAT16) return false;
+    const int vec = dtype == KF_FLOAT ? 4 : 8;
+    if (E < vec || E % vec != 0) return false;
+    if (reinterpret_cast<uintptr_t>(x) % 16 != 0 || reinterpret_cast<uintptr_t>(gain) % 16 != 0) return false;
+    return (dtype == KF_FLOAT ? ln_nv<float>(E) : ln_nv<__half>(E)) != 0;
+}
+
+template <typename T>
+static void ln_fwd_typed(const LnArgs &a) {
+    constexpr int VEC = 16 / sizeof(T);
+    Runtime &rt = Runtime::get();
+    KF_CHECK(a.rows < (int64_t)0x7FFFFFFF);
+    const unsigned grid = (unsigned)a.rows;
+    switch (ln_nv<T>(a.E)) {
+    case 1: layer_norm_fwd_kernel<T, VEC, 1><<<grid, LN_THREADS, 0, rt.stream()>>>(a); break;
+    case 2: layer_norm_fwd_kernel<T, VEC, 2><<<grid, LN_THREADS, 0, rt.stream()>>>(a); break;
+    case 4: layer_norm_fwd_kernel<T, VEC, 4><<<grid, LN_THREADS, 0, rt.stream()>>>(a); break;
+    default: layer_norm_fwd_kernel<T, VEC, 8><<<grid, LN_THREADS, 0, rt.stream()>>>(a); break;
+    }
+    rt.post_launch("layer_norm_fwd_kernel");
+}
+
+void launch_layer_norm_fwd(const void *x, const void *gain, void *y, float *mean, float *rstd, int dtype, int64_t rows, int64_t E, float eps) {
+    if (rows == 0) return;
+    LnArgs a{};
+    a.x = x; a.gain = gain; a.y = y; a.mean = mean; a.rstd = rstd; a.rows = rows; a.E = E; a.eps = eps;
+    if (dtype == KF_FLOAT) ln_fwd_typed<float>(a);
+    else if (dtype == KF_HALF) ln_fwd_typed<__half>(a);
+    else ln_fwd_typed<__nv_bfloat16>(a);
+}
+
+int layer_norm_bwd_ctas(int64_t rows) {
+    const int64_t cap = (int64_t)Runtime::get().props().sm_count * 8;  // 8 CTAs of 128 threads per SM keep enough loads in flight
+    return (int)std::max<int64_t>(1, std::min<int64_t>(rows, cap));
+}
+
+template <typename T>
+static void ln_bwd_typed(const LnArgs &a, int ctas, bool write_dx) {
+    constexpr int VEC = 16 / sizeof(T);
+    Runtime &rt = Runtime::get();
+#define KF_LN_BWD(NVV)                                                                                       \
+    do {                                                                                                     \
+        if (write_dx) layer_norm_bwd_kernel<T, VEC, NVV, true><<<ctas, LN_THREADS, 0, rt.stream()>>>(a);    \
+        else layer_norm_bwd_kernel<T, VEC, NVV, false><<<ctas, LN_THREADS, 0, rt.stream()>>>(a);            \
+    } while (0)
+    switch (ln_nv<T>(a.E)) {
+    case 1: KF_LN_BWD(1); break;
+    case 2: KF_LN_BWD(2); break;
+    case 4: KF_LN_BWD(4); break;
+    default: KF_LN_BWD(8); break;
+    }
+#undef KF_LN_BWD
+    rt.post_launch("layer_norm_bwd_kernel");
+}
+
+// dx may be null (input needs no gradient); dgain_partial is [layer_norm_bwd_ctas(rows), E] fp32
+void launch_layer_norm_bwd(const void *x, const void *gain, const void *dy, const float *mean, const float *rstd, void *dx,
+                           float *dgain_partial, int ctas, int dtype, int64_t rows, int64_t E) {
+    if (rows == 0) return;
+    LnArgs a{};
+    a.x = x; a.gain = gain; a.dy = dy; a.dx = dx; a.mean = const_cast<float *>(mean); a.rstd = const_cast<float *>(rstd);
+    a.dgain_partial = dgain_partial; a.rows = rows; a.E = E;
+    if (dtype == KF_FLOAT) ln_bwd_typed<float>(a, ctas, dx != nullptr);
+    else if (dtype == KF_HALF) ln_bwd_typed<__half>(a, ctas, dx != nullptr);
+    else ln_bwd_typed<__nv_bfloat16>(a, ctas, dx != nullptr);
+}
+
+}  // namespace kf

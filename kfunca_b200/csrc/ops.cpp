@@ -358,6 +358,61 @@ std::tuple<Tensor, Tensor> norm_stat(const Tensor &self, int64_t dim) {
     return {m, invstd};
 }
 
+// ================================================================== fused layer norm
+struct LayerNormGrad : GradFunction {
+    Tensor x, gain, stats;  // stats: fp32 [2, rows] = mean | rstd
+    int64_t rows, E;
+    const char *name() const override { return "LayerNormGrad"; }
+    std::vector<Tensor> backward(const Tensor &g0) override {
+        Tensor g = g0.is_contiguous() ? g0 : clone(g0.detach());
+        const bool need_dx = inputs[0].requires_grad();
+        Tensor dx;
+        if (need_dx) dx = empty(x.sizes(), x.dtype(), x.device());
+        const int ctas = layer_norm_bwd_ctas(rows);
+        Tensor partial = empty({(int64_t)ctas, E}, KF_FLOAT, x.device());
+        const float *st = reinterpret_cast<const float *>(stats.data());
+        launch_layer_norm_bwd(x.data(), gain.data(), g.data(), st, st + rows, need_dx ? dx.data() : nullptr,
+                              reinterpret_cast<float *>(partial.data()), ctas, x.dtype(), rows, E);
+        Tensor dgain = convert(sum(partial, 0), x.dtype()).view(gain.sizes());
+        return {dx, dgain};
+    }
+};
+
+Tensor layer_norm(const Tensor &x_, const Tensor &gain_, double eps) {
+    require_device(x_, "layer_norm");
+    require_device(gain_, "layer_norm");
+    KF_CHECK(x_.dim() >= 1 && x_.dtype() == gain_.dtype(), "layer_norm: x and gain must share a dtype");
+    const int64_t E = x_.size(-1);
+    KF_CHECK(gain_.numel() == E, "layer_norm: gain must have ", E, " elements");
+    Tensor x = x_.is_contiguous() ? x_ : contiguous(x_);
+    Tensor gain = gain_.is_contiguous() ? gain_ : contiguous(gain_);
+    if (!layer_norm_supported(x.dtype(), E, x.data(), gain.data())) {
+        // composed form (same arithmetic, several passes): rows too long for the register-resident kernels, or fp64
+        std::vector<int64_t> gshape(x.dim(), 1);
+        gshape.back() = E;
+        Tensor mu = mean(x, -1);
+        Tensor xc = binary(EW_SUB, x, mu);
+        Tensor var = mean(binary(EW_MUL, xc, xc), -1);
+        Tensor rstd = unary(EW_RSQRT, binary_scalar(EW_ADD, var, eps));
+        return binary(EW_MUL, binary(EW_MUL, xc, rstd), view(gain, gshape));
+    }
+    const int64_t rows = E ? x.numel() / E : 0;
+    Tensor out = empty(x.sizes(), x.dtype(), x.device());
+    Tensor stats = empty({2, rows}, KF_FLOAT, x.device());
+    float *st = reinterpret_cast<float *>(stats.data());
+    launch_layer_norm_fwd(x.data(), gain.data(), out.data(), st, st + rows, x.dtype(), rows, E, (float)eps);
+    if (any_requires_grad({&x, &gain})) {
+        auto *fn = new LayerNormGrad();
+        fn->x = x.detach();
+        fn->gain = gain.detach();
+        fn->stats = stats;
+        fn->rows = rows;
+        fn->E = E;
+        attach(out, fn, {x, gain});
+    }
+    return out;
+}
+
 // ================================================================== sort / top-k
 static Tensor move_dim_last(const Tensor &t, int d) {
     std::vector<int64_t> perm;

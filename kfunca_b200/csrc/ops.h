@@ -36,6 +36,9 @@ std::tuple<Tensor, Tensor> norm_stat(const Tensor &self, int64_t dim);
 // reduce `grad` (shape = broadcast result) back to `shape` by summing broadcast dims (autograd helper)
 Tensor sum_to_shape(const Tensor &grad, const std::vector<int64_t> &shape);
 
+// ---- fused layer norm over the last dim (gain has E elements); differentiable in x and gain
+Tensor layer_norm(const Tensor &x, const Tensor &gain, double eps);
+
 // ---- sort / top-k
 std::tuple<Tensor, Tensor> sort(const Tensor &self, int64_t dim, bool descending);
 std::tuple<Tensor, Tensor> topk(const Tensor &self, int64_t k, int64_t dim, bool largest);

@@ -299,6 +299,11 @@ PYBIND11_MODULE(_kfunca, m) {
         return PyTensor(h);
     });
     m.def("sqrt", [](const PyTensor &a) { kf_tensor_t h; ck(kf_unary(KF_UOP_SQRT, a.get(), &h)); return PyTensor(h); });
+    m.def("layer_norm", [](const PyTensor &x, const PyTensor &gain, double eps) {
+        kf_tensor_t h;
+        ck(kf_layer_norm(x.get(), gain.get(), eps, &h));
+        return PyTensor(h);
+    });
     m.def("rsqrt", [](const PyTensor &a) { kf_tensor_t h; ck(kf_unary(KF_UOP_RSQRT, a.get(), &h)); return PyTensor(h); });
     m.def("neg", [](const PyTensor &a) { kf_tensor_t h; ck(kf_unary(KF_UOP_NEG, a.get(), &h)); return PyTensor(h); });
     m.def("promote_types", [](kf_dtype_t a, kf_dtype_t b) { int o; ck(kf_promote_types(a, b, &o)); return (kf_dtype_t)o; });

@@ -39,10 +39,11 @@ def host(t):
     return t.float().numpy().astype(np.float64) if t.dtype() != kf.double else t.numpy()
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("dtype,B,S,E,H,tol", [("float", 2, 64, 128, 2, 2e-4), ("bfloat16", 2, 256, 256, 2, 3e-2)])
-def test_block_forward_backward_matches_torch_autograd(dtype, B, S, E, H, tol):
+def test_block_forward_backward_matches_torch_autograd(dtype, B, S, E, H, tol, fused):
     kdt = getattr(kf, dtype)
-    blk = Block(E, H, dtype=kdt, device=0, seed=3)
+    blk = Block(E, H, dtype=kdt, device=0, seed=3, fused_norm=fused)
     rng = np.random.default_rng(5)
     x_np = rng.uniform(-1, 1, (B, S, E)).astype(np.float32)
     x = kf.from_numpy(x_np, 0).to(kdt)
@@ -85,3 +86,38 @@ def test_leaf_grad_hook_fires_once_per_parameter_with_the_final_gradient():
     seen.clear()
     blk.step(x)  # hook removed: nothing recorded
     assert not seen
+
+
+@pytest.mark.parametrize("dtype,shape,tol", [("float", (37, 512), 2e-5), ("float", (3, 5, 1000), 2e-5), ("float", (130, 4096), 2e-5),
+                                             ("bfloat16", (64, 4096), 2e-2), ("half", (33, 2048), 5e-3), ("bfloat16", (7, 264), 2e-2),
+                                             ("double", (9, 96), 1e-10), ("float", (4, 8200 * 4), 2e-5)])
+def test_layer_norm_forward_backward(dtype, shape, tol):
+    """kf.layer_norm (fused kernels; composed fallback for fp64 / very long rows) against torch float64 autograd on the rounded
+    inputs: y, dx and dgain.  fp32 within 2e-5 of each quantity's scale, 16-bit within its rounding."""
+    kdt = getattr(kf, dtype)
+    rng = np.random.default_rng(11)
+    E = shape[-1]
+    x = kf.from_numpy(rng.uniform(-3, 3, shape).astype(np.float32), 0).to(kdt)
+    gshape = (1,) * (len(shape) - 1) + (E,)
+    gain = kf.from_numpy(rng.uniform(0.5, 1.5, gshape).astype(np.float32), 0).to(kdt)
+    dy = kf.from_numpy(rng.uniform(-1, 1, shape).astype(np.float32), 0).to(kdt)
+    x.set_requires_grad(True)
+    gain.set_requires_grad(True)
+    y = kf.layer_norm(x, gain, 1e-5)
+    y.backward(dy)
+    kf.synchronize()
+    tx = torch.tensor(host(x), dtype=torch.float64, requires_grad=True)
+    tg = torch.tensor(host(gain), dtype=torch.float64, requires_grad=True)
+    ty = torch.nn.functional.layer_norm(tx, (E,), weight=tg.reshape(E), eps=1e-5)
+    ty.backward(torch.tensor(host(dy), dtype=torch.float64))
+    for name, got, want in (("y", host(y), ty.detach().numpy()), ("dx", host(x.grad()), tx.grad.numpy()),
+                            ("dgain", host(gain.grad()).reshape(-1), tg.grad.numpy().reshape(-1))):
+        scale = max(np.abs(want).max(), 1e-30)
+        err = np.abs(got - want).max() / scale
+        assert got.shape == want.shape and err <= tol, (name, dtype, shape, err)
+    # input without gradient: only dgain is produced
+    x2 = kf.from_numpy(host(x).astype(np.float32), 0).to(kdt)
+    gain.zero_grad()
+    kf.layer_norm(x2, gain, 1e-5).backward(dy)
+    assert not x2.grad().defined()
+    assert np.abs(host(gain.grad()).reshape(-1) - tg.grad.numpy().reshape(-1)).max() <= tol * np.abs(tg.grad.numpy()).max()

@@ -1,10 +1,7 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-tag=s8k
-timeout 300 python -m pytest tests/test_attention_gpu.py tests/test_block_gpu.py -m gpu -x -q 2>&1 | tail -3
-for cfg in "1 2" "1 0" "1 3"; do
-  set -- $cfg
-  echo "SPLIT=$1 POLY=$2"
-  KF_ATTN_SPLIT=$1 KF_ATTN_POLY=$2 timeout 120 python tools/gpu_attn.py --parity 2>&1 | tail -5
-done | tee gpurun_out/${tag}_attn.log
+tag=s8m
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_block_launches.csv \
+   python tools/gpu_block_probe.py --once > gpurun_out/${tag}_block_ncu.log 2>&1
+tail -2 gpurun_out/${tag}_block_ncu.log

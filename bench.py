@@ -368,6 +368,7 @@ def extras(kf, Event, peaks):
     mem("c1_permute_contiguous", lambda i: A[i].permute(1, 0).contiguous(), 2 * nb)
     # fused layer norm over rows of 4096 (the block's shape class), fp32: forward reads x + writes y,
     # backward reads x, dy + writes dx (statistics and the gain gradient are < 0.1 % of the bytes)
+    mem("f1_mean_var_dim1_fp32_4096", lambda i: A[i].mean_var(1, False), nb + 2 * N * 4)  # one-pass row statistics
     gain = kf.from_numpy(rng.uniform(0.5, 1.5, (1, N)).astype(np.float32), 0)
     mem("f1_layer_norm_fwd_fp32_4096", lambda i: kf.layer_norm(A[i], gain, 1e-5), 2 * nb)
     for a_ in A:

@@ -111,6 +111,8 @@ void launch_attn_probs(void *S, const void *lse, int dtype, int64_t BH, int64_t 
 bool layer_norm_supported(int dtype, int64_t E, const void *x, const void *gain);
 void launch_layer_norm_fwd(const void *x, const void *gain, void *y, float *mean, float *rstd, int dtype, int64_t rows, int64_t E, float eps);
 int layer_norm_bwd_ctas(int64_t rows);
+// mean + unbiased variance (or its sqrt) of each dense fp32 row in ONE pass; false when the shape is not covered
+bool launch_row_moments(const void *x, void *mean, void *var, int dtype, int64_t rows, int64_t E, bool take_sqrt);
 void launch_layer_norm_bwd(const void *x, const void *gain, const void *dy, const float *mean, const float *rstd, void *dx,
                            float *dgain_partial, int ctas, int dtype, int64_t rows, int64_t E);
 

@@ -100,6 +100,49 @@ __global__ void __launch_bounds__(LN_THREADS) layer_norm_fwd_kernel(const LnArgs
     }
 }
 
+// Row statistics only (mean_var over the last dimension, ref: gpu::mean_var, src/core/reduce_ops.cpp:22-28 — Welford with
+// correction 1): same register-resident two-pass scheme, one HBM read; out_var = M2 / (E - 1), optionally its square root.
+template <typename T, int VEC, int NV>
+__global__ void __launch_bounds__(LN_THREADS) row_moments_kernel(const T *__restrict__ xin, T *__restrict__ out_mean, T *__restrict__ out_var,
+                                                                 const int64_t E, const int take_sqrt) {
+    __shared__ float red[8];
+    const int64_t row = blockIdx.x;
+    const int nvec = (int)(E / VEC);
+    const T *__restrict__ x = xin + row * E;
+    float v[NV][VEC];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int iv = threadIdx.x + k * LN_THREADS;
+        if (iv < nvec) {
+            const Pack<T, VEC> pk = ln_ld<T, VEC>(x + (int64_t)iv * VEC);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                v[k][i] = cvt_in<float>(pk.v[i]);
+                s += v[k][i];
+            }
+        }
+    }
+    const float mean = ln_block_sum(s, red) / (float)E;
+    float d = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int iv = threadIdx.x + k * LN_THREADS;
+        if (iv < nvec) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) d += (v[k][i] - mean) * (v[k][i] - mean);
+        }
+    }
+    const float m2 = ln_block_sum(d, red + 4);
+    if (threadIdx.x == 0) {
+        const float div = (float)E - 1.f;
+        float var = m2 / (div > 0.f ? div : 0.f);
+        if (take_sqrt) var = sqrtf(var);
+        out_mean[row] = cvt_out<T, float>(mean);
+        out_var[row] = cvt_out<T, float>(var);
+    }
+}
+
 // dx = rstd * (gg - mean_e(gg) - xhat * mean_e(gg * xhat)),  gg = dy * gain,  xhat = (x - mean) * rstd
 // dgain[e] = sum_rows dy * xhat  (per-CTA partial rows here, folded by the caller)
 template <typename T, int VEC, int NV, bool WRITE_DX>
@@ -218,6 +261,25 @@ void launch_layer_norm_fwd(const void *x, const void *gain, void *y, float *mean
     if (dtype == KF_FLOAT) ln_fwd_typed<float>(a);
     else if (dtype == KF_HALF) ln_fwd_typed<__half>(a);
     else ln_fwd_typed<__nv_bfloat16>(a);
+}
+
+// fp32 rows only (the reference's mean_var is fp32 / fp64); false => caller composes the statistics from sum / mean
+bool launch_row_moments(const void *x, void *mean, void *var, int dtype, int64_t rows, int64_t E, bool take_sqrt) {
+    if (dtype != KF_FLOAT || E < 4 || E % 4 != 0 || reinterpret_cast<uintptr_t>(x) % 16 != 0 || ln_nv<float>(E) == 0) return false;
+    if (rows == 0) return true;
+    KF_CHECK(rows < (int64_t)0x7FFFFFFF);
+    Runtime &rt = Runtime::get();
+    const float *xp = reinterpret_cast<const float *>(x);
+    float *mp = reinterpret_cast<float *>(mean), *vp = reinterpret_cast<float *>(var);
+    const unsigned grid = (unsigned)rows;
+    switch (ln_nv<float>(E)) {
+    case 1: row_moments_kernel<float, 4, 1><<<grid, LN_THREADS, 0, rt.stream()>>>(xp, mp, vp, E, take_sqrt); break;
+    case 2: row_moments_kernel<float, 4, 2><<<grid, LN_THREADS, 0, rt.stream()>>>(xp, mp, vp, E, take_sqrt); break;
+    case 4: row_moments_kernel<float, 4, 4><<<grid, LN_THREADS, 0, rt.stream()>>>(xp, mp, vp, E, take_sqrt); break;
+    default: row_moments_kernel<float, 4, 8><<<grid, LN_THREADS, 0, rt.stream()>>>(xp, mp, vp, E, take_sqrt); break;
+    }
+    rt.post_launch("row_moments_kernel");
+    return true;
 }
 
 int layer_norm_bwd_ctas(int64_t rows) {

@@ -336,6 +336,12 @@ std::tuple<Tensor, Tensor> mean_var(const Tensor &self, int64_t dim, bool take_s
     KF_CHECK(self.dtype() == KF_FLOAT || self.dtype() == KF_DOUBLE, "Unsupported ScalarType ", dtype_name(self.dtype()));
     const int d = wrap_dim(dim, self.dim());
     Tensor x = self.detach();
+    if (d == self.dim() - 1 && x.is_contiguous() && x.device() >= 0 && x.size(d) >= 2) {  // one-pass row statistics (kernels/norm.cu)
+        auto oshape = x.sizes();
+        oshape[d] = 1;
+        Tensor m = empty(oshape, x.dtype(), x.device()), v = empty(oshape, x.dtype(), x.device());
+        if (launch_row_moments(x.data(), m.data(), v.data(), x.dtype(), x.numel() / x.size(d), x.size(d), take_sqrt)) return {m, v};
+    }
     Tensor m = mean(x, d);
     Tensor diff = binary(EW_SUB, x, m);
     Tensor m2 = sum(binary(EW_MUL, diff, diff), d);

@@ -335,6 +335,15 @@ def test_mean_var_and_norm_stat():  # ref: test_tensor.py:120-146
     assert_close(v, arr.var(1, ddof=1, keepdims=True), rtol=1e-10, atol=1e-10)
     m, s = g(arr).mean_var(2, True)
     assert_close(s, arr.std(2, ddof=1, keepdims=True), rtol=1e-10, atol=1e-10)
+    # fp32 over the last dim: the one-pass row-statistics kernel (and the composed path for rows it does not cover)
+    for shape in ([37, 512], [5, 7, 4096], [3, 1000], [2, 16384 * 3], [4, 30]):
+        a = rand(shape)
+        a64 = a.astype(np.float64)
+        m, v = g(a).mean_var(-1, False)
+        assert_close(m, a64.mean(-1, keepdims=True), rtol=1e-5, atol=1e-5)
+        assert_close(v, a64.var(-1, ddof=1, keepdims=True), rtol=1e-5, atol=1e-6)
+        m, sd = g(a).mean_var(-1, True)
+        assert_close(sd, a64.std(-1, ddof=1, keepdims=True), rtol=1e-5, atol=1e-6)
     for shape in ([64, 64], [1024, 2048]):
         a = rand(shape)
         m, inv = g(a).norm_stat(0)

@@ -379,7 +379,9 @@ def extras(kf, Event, peaks):
         A[i].zero_grad()
         ys[i].backward(B[i])
 
-    mem("f1_layer_norm_bwd_fp32_4096", ln_bwd, 3 * nb)
+    # through the autograd engine: dx kernel + gain-gradient kernel + partial fold + the engine's copy of dx into the leaf's
+    # grad slot; the algorithmic bytes counted are only x, dy in and dx out
+    mem("f1_layer_norm_bwd_autograd_fp32_4096", ln_bwd, 3 * nb)
     del A, B, ys
     # C4 top-k at reduced row count (8192 x 32768 fp32 = 1 GiB > L2; full 65536 rows is the same kernel, 8x longer)
     rows, cols, k = 8192, 32768, 64

@@ -114,7 +114,7 @@ def barrier(dist):
 def run_ours(args):
     rank, world, dist = dist_setup(args.gpus)
     import kfunca_b200 as kf
-    from kfunca_b200.runtime import Event, PinnedBuffer, copy_from_host_async, copy_to_host_async, launch_count
+    from kfunca_b200.runtime import Event, PinnedBuffer, copy_from_host_async, copy_to_host_async, gemm_host, launch_count
     from oracle import oracle as O  # bf16 host dtype + cpu_baseline leg only
 
     peaks = measured_peaks()
@@ -138,17 +138,30 @@ def run_ours(args):
     def step():
         return kf.gemm(A, B, 1.0, 0.0)
 
-    def step_e2e():
+    def step_e2e_sequential():  # the reference user's sequence: upload a, upload b, gemm, download c — one after the other
         copy_from_host_async(A, a_host)
         copy_from_host_async(B, b_host)
         C = kf.gemm(A, B, 1.0, 0.0)
         copy_to_host_async(c_host, C)
         kf.synchronize()
 
+    def step_e2e():  # same bytes, same GEMM kernel, through the host-buffer entry point (kf_gemm_host): slabs overlap on 3 streams
+        gemm_host(c_host, a_host, b_host, kf.bfloat16)
+        kf.synchronize()
+
     for _ in range(max(args.warmup, 3)):
         step()
     kf.synchronize()
     sampler = ClockSampler(local).start() if rank == 0 else None
+    # K timed steps of 0.7 ms are shorter than one nvidia-smi period (100 ms): keep the SAME kernel running (extra, untimed
+    # warm-up launches) until the sampler has seen the GPU under this load a few times, then time the K steps without a gap —
+    # the samples bracket the timed region and the clocks they show are the ones it ran at
+    if sampler is not None and sampler.proc is not None:
+        t_guard = time.perf_counter()
+        while len(sampler.rows) < 4 and time.perf_counter() - t_guard < 3.0:
+            for _ in range(20):
+                step()
+            kf.synchronize()
     barrier(dist)
     kf.synchronize()
     l0 = launch_count()
@@ -179,6 +192,13 @@ def run_ours(args):
     e2e_ms = max_over_ranks(e0.elapsed_ms(e1), dist) / e2e_steps
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     e2e_val = world * flops / (max(e2e_ms, e2e_wall_ms) * 1e-3) / 1e12
+    # the e2e result must be the same product: compare the downloaded C with the device-resident path (bit-identical kernel)
+    e2e_same = bool(np.array_equal(c_host.array, kf.gemm(A, B, 1.0, 0.0).numpy().view(np.uint16)))
+    step_e2e_sequential()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        step_e2e_sequential()
+    seq_ms = (time.perf_counter() - t0) * 1e3 / 3
 
     # at N > 1 the C5 block (the only workload with a real exchange step) is timed after the headline on all ranks and
     # attached to the same JSON line as extras.c5_block, so the driver's scaling run records it
@@ -206,7 +226,8 @@ def run_ours(args):
                    "l2": "A+B = 256 MiB > 126 MB L2, no flush needed", "seed": 1234, "parity_spot_check": parity_ok,
                    "parallelism": f"dp{world} (independent M-slabs, no collective)"},
         "e2e": {"value": round(e2e_val, 2), "unit": "TFLOP/s", "h2d_bytes_per_step": 2 * n * n * 2, "d2h_bytes_per_step": n * n * 2,
-                "ms_per_step": round(max(e2e_ms, e2e_wall_ms), 3)},
+                "ms_per_step": round(max(e2e_ms, e2e_wall_ms), 3), "api": "kf_gemm_host (pinned host A, B, C; upload / slab GEMM / download overlapped)",
+                "matches_device_path": e2e_same, "sequential_ms_per_step": round(seq_ms, 3)},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),

@@ -160,6 +160,12 @@ int kf_index_put_(kf_tensor_t self, const kf_tensor_t *indices, int n, kf_tensor
 /* out[...,N] = alpha * a[...,K] @ b[K,N] (+ beta*out for kf_gemm_out); fp32/fp64 SIMT, fp16/bf16 tcgen05 */
 int kf_gemm(kf_tensor_t a, kf_tensor_t b, float alpha, float beta, kf_tensor_t *out);
 int kf_gemm_out(kf_tensor_t out, kf_tensor_t a, kf_tensor_t b, float alpha, float beta);
+/* gemm with operands and result in HOST memory (row-major, contiguous; pin them with kf_host_alloc_pinned for full PCIe rate):
+ * the path a kfunca user writes as from_numpy(a), from_numpy(b), gemm, numpy() (register.cpp:27-57,86 around gemm_ops.cpp:10-16),
+ * with the upload of A in M-slabs, the slab products and the download of C overlapped on three streams.  Asynchronous:
+ * the library stream is ordered after all of it, kf_synchronize() makes c_host readable.  slab_rows <= 0 picks 1024. */
+int kf_gemm_host(const void *a_host, const void *b_host, void *c_host, int64_t M, int64_t N, int64_t K, int dtype, float alpha,
+                 int64_t slab_rows);
 /* general form used by the backward passes: op(a) is a or a^T over the last two dims, batched over leading dims */
 int kf_matmul(kf_tensor_t a, int trans_a, kf_tensor_t b, int trans_b, float alpha, kf_tensor_t *out);
 /* q,k,v: [B,H,S,D] contiguous; top-left-aligned causal mask, scale 1/sqrt(D) (ref: causal_attention_kernel.cu:9-72) */

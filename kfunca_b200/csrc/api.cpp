@@ -502,6 +502,12 @@ int kf_causal_attention_bwd(kf_tensor_t dout, kf_tensor_t q, kf_tensor_t k, kf_t
     KF_API_END
 }
 
+int kf_gemm_host(const void *a_host, const void *b_host, void *c_host, int64_t M, int64_t N, int64_t K, int dtype, float alpha,
+                 int64_t slab_rows) {
+    KF_API_BEGIN
+    ops::gemm_host(a_host, b_host, c_host, M, N, K, (DType)dtype, alpha, slab_rows);
+    KF_API_END
+}
 int kf_layer_norm(kf_tensor_t x, kf_tensor_t gain, double eps, kf_tensor_t *out) {
     KF_API_BEGIN
     *out = wrap(ops::layer_norm(T(x), T(gain), eps));

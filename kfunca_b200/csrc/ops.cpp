@@ -761,6 +761,68 @@ Tensor gemm(const Tensor &a, const Tensor &b, float alpha, float beta) {
     return matmul(a, false, b, false, alpha);
 }
 
+// Host-resident GEMM: C_host[M,N] = alpha * A_host[M,K] @ B_host[K,N], operands and result in (pinned) host memory.
+// The reference's user pays H2D(A) + H2D(B) + GEMM + D2H(C) back to back (register.cpp:27-57 around gemm); PCIe is full duplex,
+// so here B goes up first on a copy stream, then A in M-slabs; each slab's product is computed on the library stream as soon as
+// it has landed and comes down on a second copy stream while the next slab goes up.  Lower bound = H2D(A + B); the D2H and the
+// GEMM hide under it except for the last slab.  Two device slabs of A and of C are recycled through events.
+void gemm_host(const void *a_host, const void *b_host, void *c_host, int64_t M, int64_t N, int64_t K, DType dtype, float alpha,
+               int64_t slab_rows) {
+    KF_CHECK(a_host && b_host && c_host && M > 0 && N > 0 && K > 0, "gemm_host: bad arguments");
+    KF_CHECK(dtype == KF_HALF || dtype == KF_BFLOAT16 || dtype == KF_FLOAT || dtype == KF_DOUBLE, "gemm_host: floating dtypes only");
+    Runtime &rt = Runtime::get();
+    static cudaStream_t up = nullptr, down = nullptr;
+    static cudaEvent_t ev_b = nullptr, a_ready[2], a_free[2], c_ready[2], c_free[2];
+    if (!up) {
+        KF_CUDA(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+        KF_CUDA(cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking));
+        KF_CUDA(cudaEventCreateWithFlags(&ev_b, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) {
+            KF_CUDA(cudaEventCreateWithFlags(&a_ready[i], cudaEventDisableTiming));
+            KF_CUDA(cudaEventCreateWithFlags(&a_free[i], cudaEventDisableTiming));
+            KF_CUDA(cudaEventCreateWithFlags(&c_ready[i], cudaEventDisableTiming));
+            KF_CUDA(cudaEventCreateWithFlags(&c_free[i], cudaEventDisableTiming));
+        }
+    }
+    const size_t es = element_size(dtype);
+    if (slab_rows <= 0) slab_rows = 1024;
+    slab_rows = std::min(slab_rows, M);
+    const int dev = rt.device();
+    Tensor dB = empty({K, N}, dtype, dev);
+    Tensor dA[2] = {empty({slab_rows, K}, dtype, dev), empty({slab_rows, K}, dtype, dev)};
+    Tensor dC[2] = {empty({slab_rows, N}, dtype, dev), empty({slab_rows, N}, dtype, dev)};
+    // the copy streams start after everything already queued on the library stream (the pool hands out memory in its order)
+    KF_CUDA(cudaEventRecord(ev_b, rt.stream()));
+    KF_CUDA(cudaStreamWaitEvent(up, ev_b, 0));
+    KF_CUDA(cudaStreamWaitEvent(down, ev_b, 0));
+    KF_CUDA(cudaMemcpyAsync(dB.data(), b_host, (size_t)K * N * es, cudaMemcpyHostToDevice, up));
+    KF_CUDA(cudaEventRecord(ev_b, up));
+    KF_CUDA(cudaStreamWaitEvent(rt.stream(), ev_b, 0));
+    int s = 0;
+    for (int64_t m0 = 0; m0 < M; m0 += slab_rows, ++s) {
+        const int i = s & 1;
+        const int64_t rows = std::min(slab_rows, M - m0);
+        if (s >= 2) KF_CUDA(cudaStreamWaitEvent(up, a_free[i], 0));  // the product that read this A slab has run
+        KF_CUDA(cudaMemcpyAsync(dA[i].data(), (const char *)a_host + (size_t)m0 * K * es, (size_t)rows * K * es, cudaMemcpyHostToDevice, up));
+        KF_CUDA(cudaEventRecord(a_ready[i], up));
+        KF_CUDA(cudaStreamWaitEvent(rt.stream(), a_ready[i], 0));
+        if (s >= 2) KF_CUDA(cudaStreamWaitEvent(rt.stream(), c_free[i], 0));  // the download of this C slab's previous tenant is done
+        Tensor av = rows == slab_rows ? dA[i] : dA[i].slice(0, 0, rows, 1);
+        Tensor cv = rows == slab_rows ? dC[i] : dC[i].slice(0, 0, rows, 1);
+        matmul_nograd(av, false, dB, false, alpha, 0.f, &cv);
+        KF_CUDA(cudaEventRecord(a_free[i], rt.stream()));
+        KF_CUDA(cudaEventRecord(c_ready[i], rt.stream()));
+        KF_CUDA(cudaStreamWaitEvent(down, c_ready[i], 0));
+        KF_CUDA(cudaMemcpyAsync((char *)c_host + (size_t)m0 * N * es, dC[i].data(), (size_t)rows * N * es, cudaMemcpyDeviceToHost, down));
+        KF_CUDA(cudaEventRecord(c_free[i], down));
+    }
+    // join: later work on the library stream (and the pool's stream-ordered frees of dA / dB / dC) follows both copy streams
+    KF_CUDA(cudaEventRecord(ev_b, up));
+    KF_CUDA(cudaStreamWaitEvent(rt.stream(), ev_b, 0));
+    KF_CUDA(cudaStreamWaitEvent(rt.stream(), c_free[0], 0));
+    if (s >= 2) KF_CUDA(cudaStreamWaitEvent(rt.stream(), c_free[1], 0));
+}
+
 void gemm_out(Tensor &out, const Tensor &a, const Tensor &b, float alpha, float beta) {
     KF_CHECK(out.is_contiguous() && a.is_contiguous() && b.is_contiguous());
     KF_CHECK(b.dim() == 2 && b.size(0) == a.size(-1));

@@ -57,6 +57,9 @@ Tensor slice(const Tensor &self, int64_t dim, int64_t start, int64_t end, int64_
 Tensor gemm(const Tensor &a, const Tensor &b, float alpha, float beta);
 void gemm_out(Tensor &out, const Tensor &a, const Tensor &b, float alpha, float beta);
 Tensor matmul(const Tensor &a, bool trans_a, const Tensor &b, bool trans_b, float alpha);
+// operands and result in (pinned) host memory; uploads, slab products and downloads overlap on three streams
+void gemm_host(const void *a_host, const void *b_host, void *c_host, int64_t M, int64_t N, int64_t K, DType dtype, float alpha,
+               int64_t slab_rows);
 Tensor causal_attention(const Tensor &q, const Tensor &k, const Tensor &v);
 std::tuple<Tensor, Tensor> causal_attention_fwd(const Tensor &q, const Tensor &k, const Tensor &v);
 std::tuple<Tensor, Tensor, Tensor> causal_attention_bwd(const Tensor &dout, const Tensor &q, const Tensor &k, const Tensor &v,

@@ -93,3 +93,15 @@ def copy_to_host_async(pinned: PinnedBuffer, tensor) -> None:
     """D2H of a contiguous `tensor` into a pinned buffer on the library stream, no sync (kf_memcpy_d2h_async)."""
     assert tensor.is_contiguous() and tensor.numel() * pinned.dtype.itemsize == pinned.nbytes
     _ck(_lib.kf_memcpy_d2h_async(ctypes.c_void_p(pinned.ptr), ctypes.c_void_p(tensor.data_ptr()), ctypes.c_size_t(pinned.nbytes)))
+
+
+def gemm_host(c: PinnedBuffer, a: PinnedBuffer, b: PinnedBuffer, dtype, alpha: float = 1.0, slab_rows: int = 0) -> None:
+    """c = alpha * a @ b with all three operands in pinned HOST memory (kf_gemm_host): B is uploaded once, A streams up in
+    M-slabs, each slab's product runs on the library stream and comes down while the next slab goes up.  Asynchronous —
+    call kf.synchronize() before reading `c`.  `dtype` is the kfunca dtype of the buffers (their NumPy dtype may be a raw
+    16-bit view of bf16 data)."""
+    M, K = a.shape
+    K2, N = b.shape
+    assert K == K2 and c.shape == (M, N)
+    _ck(_lib.kf_gemm_host(ctypes.c_void_p(a.ptr), ctypes.c_void_p(b.ptr), ctypes.c_void_p(c.ptr), ctypes.c_int64(M), ctypes.c_int64(N),
+                          ctypes.c_int64(K), ctypes.c_int(int(dtype)), ctypes.c_float(alpha), ctypes.c_int64(slab_rows)))

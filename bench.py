@@ -51,11 +51,11 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.rows, self.stamps, self.proc, self.idx = [], [], None, gpu_index
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -65,12 +65,25 @@ class ClockSampler:
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
+            self.stamps.append(time.perf_counter())
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """summary of the samples that arrived inside [t0, t1] (the timed region, host clock; one sampling period of slack at the
+        end because a row describes the interval before it); without a window, of all samples"""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.08)
         self.proc.terminate()
+        rows = list(zip(self.stamps, self.rows))
+        if t0 is not None:
+            inside = [r for ts, r in rows if t0 <= ts <= t1 + 0.045]
+            if not inside:  # region shorter than the sampler's real period: take the first sample after it started
+                later = [r for ts, r in rows if ts >= t0]
+                inside = later[:1]
+            rows_sel = inside
+        else:
+            rows_sel = [r for _, r in rows]
+        self.rows = rows_sel
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -120,6 +133,9 @@ def run_ours(args):
     peaks = measured_peaks()
     local = int(os.environ.get("LOCAL_RANK", 0))
     kf.set_device(local)
+    # nvidia-smi needs ~100 ms before its first row: start it now (20 ms period) so rows are already streaming when the ~40 ms
+    # timed region runs; the rows that arrive inside the region are the ones reported
+    sampler = ClockSampler(local).start() if rank == 0 else None
     rng = np.random.default_rng(1234 + rank)
     n = N_GEMM
     # synthetic inputs: U(-1,1) -> fp32 -> bf16; A and B together are 256 MiB > the 126 MB L2
@@ -152,29 +168,21 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step()
     kf.synchronize()
-    sampler = ClockSampler(local).start() if rank == 0 else None
-    # K timed steps of 0.7 ms are shorter than one nvidia-smi period (100 ms): keep the SAME kernel running (extra, untimed
-    # warm-up launches) until the sampler has seen the GPU under this load a few times, then time the K steps without a gap —
-    # the samples bracket the timed region and the clocks they show are the ones it ran at
-    if sampler is not None and sampler.proc is not None:
-        t_guard = time.perf_counter()
-        while len(sampler.rows) < 4 and time.perf_counter() - t_guard < 3.0:
-            for _ in range(20):
-                step()
-            kf.synchronize()
     barrier(dist)
     kf.synchronize()
     l0 = launch_count()
     e0, e1 = Event(), Event()
+    t_region0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     e1.synchronize()
+    t_region1 = time.perf_counter()
     barrier(dist)
     launches = launch_count() - l0
     ms_total = max_over_ranks(e0.elapsed_ms(e1), dist)
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_region0, t_region1) if sampler else None
     ms_step = ms_total / args.steps
     value = world * flops / (ms_step * 1e-3) / 1e12
 

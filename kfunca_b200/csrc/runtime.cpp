@@ -43,7 +43,7 @@ Pool::~Pool() {
 }
 
 void *Pool::allocate(size_t bytes) {
-    std::lock_guard<std::mutex> g(mu_);
+    std::unique_lock<std::mutex> g(mu_);
     const size_t size = round_size(bytes);
     const bool small = size <= kSmallLimit;
     auto &fl = small ? free_small_ : free_large_;
@@ -72,9 +72,9 @@ void *Pool::allocate(size_t bytes) {
             raw = raw_alloc_(asz, ctx_);
         }
         if (!raw) {  // out of memory: give cached arenas back and retry once
-            mu_.unlock();
+            g.unlock();  // empty_cache() takes the mutex itself; unique_lock keeps the unlock exception-safe
             empty_cache();
-            mu_.lock();
+            g.lock();
             raw = raw_alloc_(asz, ctx_);
             KF_CHECK(raw != nullptr, "out of device memory allocating ", asz, " bytes (in use ", in_use_, ", reserved ", reserved_, ")");
         }

@@ -1,5 +1,9 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gemm_gpu.py -m gpu -x -q -k "gemm_host" 2>&1 | tail -3
-timeout 300 python bench.py --no-extras > gpurun_out/s8p_bench.json 2> gpurun_out/s8p_bench.err; tail -2 gpurun_out/s8p_bench.err; cat gpurun_out/s8p_bench.json
+tag=r1e
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${tag}_pytest.log
+tail -3 gpurun_out/${tag}_pytest.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 600 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err; echo "ref rc=$?"

@@ -1,9 +1,7 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-tag=r1e
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${tag}_pytest.log
-tail -3 gpurun_out/${tag}_pytest.log
-timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 600 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err; echo "ref rc=$?"
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29544"
+timeout 200 $TR bench.py --gpus 2 --steps 20 --warmup 5 2> gpurun_out/s8q_n2.err | tee gpurun_out/s8q_bench_n2.json | cut -c1-300
+grep "block rank 0" gpurun_out/s8q_n2.err | cut -c1-300
+timeout 100 $TR bench.py --impl reference --gpus 2 --steps 2 --warmup 1 2>/dev/null | cut -c1-200

@@ -264,3 +264,38 @@ def causal_attention_bwd(q, k, v, dout):
 def l1_tolerance_ok(got: np.ndarray, exact: np.ndarray, l1_mass: np.ndarray, rel: float) -> bool:
     """|got - exact| <= rel * sum|terms| — the well-conditioned form of "within rel" (SURVEY §8d)."""
     return bool(np.all(np.abs(got.astype(np.float64) - exact) <= rel * l1_mass + 1e-30))
+
+
+def mean_var(x: np.ndarray, dim: int, take_sqrt: bool = False):
+    """mean and UNBIASED variance (correction 1) along `dim`, keepdim, in float64 — the reference's Welford result
+    (src/device/reduce_ops_kernel.cu:61-153, `MeanVarOps` with correction 1; src/core/reduce_ops.cpp:22-28)."""
+    x64 = np.asarray(x).astype(np.float64)
+    m = x64.mean(axis=dim, keepdims=True)
+    v = x64.var(axis=dim, ddof=1, keepdims=True)
+    return m, (np.sqrt(v) if take_sqrt else v)
+
+
+def layer_norm(x: np.ndarray, gain: np.ndarray, eps: float = 1e-5) -> np.ndarray:
+    """y = (x - mean) / sqrt(var_biased + eps) * gain over the last dim, float64.  The statistics are those of the
+    reference's norm_stat (biased variance, rsqrt(var + eps); src/device/norm_ops_kernel.cu:6-61,
+    src/device/utils/welford_norm.h:25-355); the fused op itself is the reference's next planned op (README.md:28)."""
+    x64 = np.asarray(x).astype(np.float64)
+    g64 = np.asarray(gain).astype(np.float64).reshape(-1)
+    m = x64.mean(axis=-1, keepdims=True)
+    v = ((x64 - m) ** 2).mean(axis=-1, keepdims=True)
+    return (x64 - m) / np.sqrt(v + eps) * g64
+
+
+def layer_norm_bwd(x: np.ndarray, gain: np.ndarray, dy: np.ndarray, eps: float = 1e-5):
+    """gradients of layer_norm in float64: dx (same shape as x) and dgain ([E])."""
+    x64 = np.asarray(x).astype(np.float64)
+    g64 = np.asarray(gain).astype(np.float64).reshape(-1)
+    dy64 = np.asarray(dy).astype(np.float64)
+    m = x64.mean(axis=-1, keepdims=True)
+    v = ((x64 - m) ** 2).mean(axis=-1, keepdims=True)
+    rstd = 1.0 / np.sqrt(v + eps)
+    xh = (x64 - m) * rstd
+    gg = dy64 * g64
+    dx = rstd * (gg - gg.mean(axis=-1, keepdims=True) - xh * (gg * xh).mean(axis=-1, keepdims=True))
+    dgain = (dy64 * xh).reshape(-1, x64.shape[-1]).sum(axis=0)
+    return dx, dgain

@@ -110,6 +110,12 @@ def test_layer_norm_forward_backward(dtype, shape, tol):
     tg = torch.tensor(host(gain), dtype=torch.float64, requires_grad=True)
     ty = torch.nn.functional.layer_norm(tx, (E,), weight=tg.reshape(E), eps=1e-5)
     ty.backward(torch.tensor(host(dy), dtype=torch.float64))
+    # the oracle restatement agrees with torch (tests/test_oracle.py); check the kernel against it directly as well
+    oy = O.layer_norm(host(x), host(gain), 1e-5)
+    odx, odg = O.layer_norm_bwd(host(x), host(gain), host(dy), 1e-5)
+    assert np.abs(host(y) - oy).max() <= tol * max(np.abs(oy).max(), 1e-30)
+    assert np.abs(host(x.grad()) - odx).max() <= tol * max(np.abs(odx).max(), 1e-30)
+    assert np.abs(host(gain.grad()).reshape(-1) - odg).max() <= tol * max(np.abs(odg).max(), 1e-30)
     for name, got, want in (("y", host(y), ty.detach().numpy()), ("dx", host(x.grad()), tx.grad.numpy()),
                             ("dgain", host(gain.grad()).reshape(-1), tg.grad.numpy().reshape(-1))):
         scale = max(np.abs(want).max(), 1e-30)

@@ -144,3 +144,27 @@ def test_oracle_casts_16bit():
     np.testing.assert_array_equal(O.cast(x, O.HALF), x.astype(np.float32).astype(np.float16))
     np.testing.assert_array_equal(O.cast(x, O.BFLOAT16), x.astype(np.float32).astype(O.bfloat16))
     assert float(O.scalar_through(O.HALF, 2.5)) == 2.5 and int(O.scalar_through(O.INT, 2.9)) == 2
+
+
+def test_oracle_layer_norm_and_mean_var_vs_torch():
+    """the oracle's layer_norm / layer_norm_bwd / mean_var against torch-CPU float64 (the way the reference's own tests pin
+    their expectations: recomputed from a library at test time, test/test_tensor.py:120-146)"""
+    import torch
+
+    rng = np.random.default_rng(21)
+    x = rng.uniform(-3, 3, (5, 7, 96))
+    gain = rng.uniform(0.5, 1.5, (96,))
+    dy = rng.uniform(-1, 1, x.shape)
+    tx = torch.tensor(x, requires_grad=True)
+    tg = torch.tensor(gain, requires_grad=True)
+    ty = torch.nn.functional.layer_norm(tx, (96,), weight=tg, eps=1e-5)
+    ty.backward(torch.tensor(dy))
+    np.testing.assert_allclose(O.layer_norm(x, gain, 1e-5), ty.detach().numpy(), rtol=1e-12, atol=1e-12)
+    dx, dgain = O.layer_norm_bwd(x, gain, dy, 1e-5)
+    np.testing.assert_allclose(dx, tx.grad.numpy(), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(dgain, tg.grad.numpy(), rtol=1e-10, atol=1e-12)
+    m, v = O.mean_var(x, 1)
+    np.testing.assert_allclose(m, torch.tensor(x).mean(1, keepdim=True).numpy(), rtol=1e-12)
+    np.testing.assert_allclose(v, torch.tensor(x).var(1, unbiased=True, keepdim=True).numpy(), rtol=1e-12)
+    _, sd = O.mean_var(x, 2, True)
+    np.testing.assert_allclose(sd, torch.tensor(x).std(2, unbiased=True, keepdim=True).numpy(), rtol=1e-12)

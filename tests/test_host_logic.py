@@ -193,3 +193,12 @@ def test_compute_without_gpu_fails_loudly():
                lambda: a.sort(0, False), lambda: kf.gemm(a, a, 1.0, 0.0)):
         with pytest.raises(RuntimeError):
             fn()
+
+
+def test_leaf_grad_hook_registration_needs_no_gpu():
+    """installing / removing the data-parallel leaf-gradient hook is pure host state (the hook only fires inside backward())"""
+    calls = []
+    kf.set_leaf_grad_hook(lambda leaf, grad: calls.append(1))
+    kf.set_leaf_grad_hook(None)
+    kf.set_leaf_grad_hook(None)  # idempotent
+    assert calls == []

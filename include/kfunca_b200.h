@@ -180,6 +180,25 @@ int kf_causal_attention_bwd(kf_tensor_t dout, kf_tensor_t q, kf_tensor_t k, kf_t
  * src/device/reduce_ops_kernel.cu:61-153, src/device/norm_ops_kernel.cu:6-61) and lists the fused norm as its next op
  * (README.md:28); SURVEY §8f rank 1. */
 int kf_layer_norm(kf_tensor_t x, kf_tensor_t gain, double eps, kf_tensor_t *out);
+/* y = x / sqrt(mean(x^2) + eps) * gain over the last dimension, same kernels as kf_layer_norm without the centring; the op the
+ * reference's README names as its next one (ref: README.md:28 `rms_norm`; statistics: src/device/reduce_ops_kernel.cu:61-153). */
+int kf_rms_norm(kf_tensor_t x, kf_tensor_t gain, double eps, kf_tensor_t *out);
+
+/* ---- fused linear ops (ref: README.md:32 `qkv_linear`, src/core/gemm_ops.cpp:6-16) ---------------------- */
+/* out = alpha * a[...,K] @ b[K,N] + residual[...,N]: the residual add runs in the GEMM epilogue; bit-identical to kf_gemm + kf_binary(ADD) */
+int kf_gemm_residual(kf_tensor_t a, kf_tensor_t b, kf_tensor_t residual, float alpha, kf_tensor_t *out);
+/* out = (a @ b1) * (a @ b3), the bilinear GLU, as ONE dual-B tcgen05 kernel (fp16 / bf16; other dtypes and small shapes are composed) */
+int kf_gemm_glu(kf_tensor_t a, kf_tensor_t b1, kf_tensor_t b3, kf_tensor_t *out);
+
+/* ---- embedding (ref: README.md:30 `embedding`, gather/scatter of src/device/utils/tensor_index.h:19-143,
+ * src/core/index_ops.cpp:6-38) --------------------------------------------------------------------------------------------- */
+/* out[..., :] = weight[indices[...], :] (indices int64, negative wraps); differentiable in weight: the backward is a deterministic
+ * scatter-add (stable sort of the ids, runs summed in position order, no atomics) */
+int kf_embedding(kf_tensor_t weight, kf_tensor_t indices, kf_tensor_t *out);
+
+/* counter-based uniform fill in place: element i = lo + (hi - lo) * u(i, seed), reproducible on the host (oracle.counter_uniform).
+ * Test / bench input generator for the BASELINE-size tensors (no reference counterpart; the reference's tests draw NumPy data). */
+int kf_random_uniform_(kf_tensor_t self, uint64_t seed, double lo, double hi);
 
 /* ---- autograd (ref: GradFunction/backward, tensor.h:18-22, tensor.cpp:71-126) -------------- */
 int kf_requires_grad(kf_tensor_t self, int *out);

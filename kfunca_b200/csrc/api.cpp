@@ -318,7 +318,11 @@ int kf_to_string(kf_tensor_t self, char *buf, size_t n) {
 // ---------------------------------------------------------------- views
 int kf_as_strided(kf_tensor_t self, const int64_t *sizes, const int64_t *strides, int ndim, int64_t off, kf_tensor_t *out) {
     KF_API_BEGIN
-    *out = wrap(T(self).as_strided(vec(sizes, ndim), strides ? vec(strides, ndim) : std::vector<int64_t>{}, off));
+    // a raw restride has no gradient formula: the result is a constant view (requires_grad cleared) instead of a tensor that
+    // claims to need a gradient but has no edge back to `self`
+    Tensor v = T(self).as_strided(vec(sizes, ndim), strides ? vec(strides, ndim) : std::vector<int64_t>{}, off);
+    v.impl->requires_grad = false;
+    *out = wrap(v);
     KF_API_END
 }
 int kf_permute(kf_tensor_t self, const int64_t *dims, int ndim, kf_tensor_t *out) {
@@ -338,12 +342,12 @@ int kf_slice(kf_tensor_t self, int64_t dim, int64_t start, int64_t end, int64_t 
 }
 int kf_select(kf_tensor_t self, int64_t dim, int64_t index, kf_tensor_t *out) {
     KF_API_BEGIN
-    *out = wrap(T(self).select(dim, index));
+    *out = wrap(ops::select(T(self), dim, index));
     KF_API_END
 }
 int kf_narrow(kf_tensor_t self, int64_t dim, int64_t start, int64_t length, kf_tensor_t *out) {
     KF_API_BEGIN
-    *out = wrap(T(self).narrow(dim, start, length));
+    *out = wrap(ops::narrow(T(self), dim, start, length));
     KF_API_END
 }
 int kf_split(kf_tensor_t self, const int64_t *sizes, int n, int64_t dim, kf_tensor_t *outs) {
@@ -511,6 +515,31 @@ int kf_gemm_host(const void *a_host, const void *b_host, void *c_host, int64_t M
 int kf_layer_norm(kf_tensor_t x, kf_tensor_t gain, double eps, kf_tensor_t *out) {
     KF_API_BEGIN
     *out = wrap(ops::layer_norm(T(x), T(gain), eps));
+    KF_API_END
+}
+int kf_rms_norm(kf_tensor_t x, kf_tensor_t gain, double eps, kf_tensor_t *out) {
+    KF_API_BEGIN
+    *out = wrap(ops::rms_norm(T(x), T(gain), eps));
+    KF_API_END
+}
+int kf_gemm_residual(kf_tensor_t a, kf_tensor_t b, kf_tensor_t residual, float alpha, kf_tensor_t *out) {
+    KF_API_BEGIN
+    *out = wrap(ops::gemm_residual(T(a), T(b), T(residual), alpha));
+    KF_API_END
+}
+int kf_gemm_glu(kf_tensor_t a, kf_tensor_t b1, kf_tensor_t b3, kf_tensor_t *out) {
+    KF_API_BEGIN
+    *out = wrap(ops::gemm_glu(T(a), T(b1), T(b3)));
+    KF_API_END
+}
+int kf_embedding(kf_tensor_t weight, kf_tensor_t indices, kf_tensor_t *out) {
+    KF_API_BEGIN
+    *out = wrap(ops::embedding(T(weight), T(indices)));
+    KF_API_END
+}
+int kf_random_uniform_(kf_tensor_t self, uint64_t seed, double lo, double hi) {
+    KF_API_BEGIN
+    ops::random_uniform_(T(self), seed, lo, hi);
     KF_API_END
 }
 // ---------------------------------------------------------------- autograd

@@ -69,6 +69,13 @@ bool launch_topk_rows(const void *in, void *values, int64_t *indices, int dtype,
 void launch_index_put(void *self, int dtype, const int64_t *self_shape, const int64_t *self_stride, int nidx, int64_t inner,
                       const int64_t *const *idx_ptrs, const void *values, int64_t n);
 
+// embedding gather / deterministic scatter-add (kernels/misc.cu)
+void launch_embedding_fwd(const void *weight, const int64_t *idx, void *out, int dtype, int64_t n, int64_t V, int64_t E);
+void launch_embedding_bwd(const void *grad, const int64_t *sorted_idx, const int64_t *sorted_pos, void *dweight, int dtype, int64_t n, int64_t V,
+                          int64_t E);
+// element i = lo + (hi - lo) * ((mix64(i, seed) >> 40) * 2^-24), fp32 arithmetic with separate multiply and add, then cast
+void launch_fill_random(void *p, int dtype, int64_t n, uint64_t seed, float lo, float hi);
+
 // GEMM: C[b][M,N] = alpha * op(A)[b][M,K] @ op(B)[b][K,N] + beta * C.  Row-major storage with leading
 // dimensions in elements; trans flag = operand is stored as [K,M] / [N,K].  batch strides in elements (0 = broadcast).
 struct GemmPlan {
@@ -80,9 +87,17 @@ struct GemmPlan {
     int64_t sa, sb, sc;
     int trans_a, trans_b;
     float alpha, beta;
+    // fused epilogues: C = alpha * op(A) op(B) + beta * C + residual  (residual: C's dtype, leading dim ldr)
+    const void *residual = nullptr;
+    int64_t ldr = 0, sr = 0;
+    // GLU: b2 = second B operand (same layout / ldb as b); C = (A b) o (A b2); glu_u / glu_v (C's layout) receive the two factors
+    const void *b2 = nullptr;
+    void *glu_u = nullptr, *glu_v = nullptr;
 };
+bool launch_gemm_glu_tc(const GemmPlan &p);  // false => compose from two GEMMs and a multiply
 void launch_gemm_simt(const GemmPlan &p);  // fp32 / fp64 FFMA/DFMA path (strict-parity path)
 bool launch_gemm_tc(const GemmPlan &p);    // fp16 / bf16 tcgen05 + TMEM + TMA path; false if shape unsupported
+bool launch_gemm_f32_tc(const GemmPlan &p);  // fp32 on tcgen05 through three bf16 planes per operand (6 / 9 products); false => SIMT
 void launch_gemm(const GemmPlan &p);       // dispatcher
 
 // Causal attention (top-left aligned mask, scale 1/sqrt(D)); q [BH,Sq,D], k/v [BH,Skv,D] dense.
@@ -109,12 +124,16 @@ void launch_attn_probs(void *S, const void *lse, int dtype, int64_t BH, int64_t 
 // Fused layer normalisation over the last dimension (kernels/norm.cu): y = (x - mean) * rstd * gain with biased variance.
 // `layer_norm_supported` is false for dtypes / row lengths the register-resident kernels do not cover (caller composes the op).
 bool layer_norm_supported(int dtype, int64_t E, const void *x, const void *gain);
-void launch_layer_norm_fwd(const void *x, const void *gain, void *y, float *mean, float *rstd, int dtype, int64_t rows, int64_t E, float eps);
+void launch_layer_norm_fwd(const void *x, const void *gain, void *y, float *mean, float *rstd, int dtype, int64_t rows, int64_t E, float eps,
+                           bool rms = false);
+// one-launch column statistics over [outer, R, inner] fp32 (kernels/norm.cu): mode 0 = norm_stat (mean, invstd), mode 1 = mean_var
+bool launch_col_moments(const void *x, void *out0, void *out1, int dtype, int64_t outer, int64_t R, int64_t inner, int mode, bool take_sqrt,
+                        double eps);
 int layer_norm_bwd_ctas(int64_t rows);
 // mean + unbiased variance (or its sqrt) of each dense fp32 row in ONE pass; false when the shape is not covered
 bool launch_row_moments(const void *x, void *mean, void *var, int dtype, int64_t rows, int64_t E, bool take_sqrt);
 void launch_layer_norm_bwd(const void *x, const void *gain, const void *dy, const float *mean, const float *rstd, void *dx,
-                           float *dgain_partial, int ctas, int dtype, int64_t rows, int64_t E);
+                           float *dgain_partial, int ctas, int dtype, int64_t rows, int64_t E, bool rms = false);
 
 std::string device_info_string();
 

@@ -89,6 +89,8 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_simt_kernel(const 
             if (gn >= p.N) continue;
             A v = alpha * acc[i][j];
             if (p.beta != 0.f) v += beta * to_acc<T, A>(Cb[gm * p.ldc + gn]);
+            // + residual: the product is rounded to the storage dtype first, like the unfused gemm-then-add it replaces
+            if (p.residual) v = to_acc<T, A>(cvt_out<T, A>(v)) + to_acc<T, A>(reinterpret_cast<const T *>(p.residual)[batch * p.sr + gm * p.ldr + gn]);
             Cb[gm * p.ldc + gn] = cvt_out<T, A>(v);
         }
     }
@@ -115,6 +117,7 @@ void launch_gemm_simt(const GemmPlan &p) {
 
 void launch_gemm(const GemmPlan &p) {
     if ((p.dtype == KF_HALF || p.dtype == KF_BFLOAT16) && launch_gemm_tc(p)) return;
+    if (p.dtype == KF_FLOAT && launch_gemm_f32_tc(p)) return;
     launch_gemm_simt(p);
 }
 

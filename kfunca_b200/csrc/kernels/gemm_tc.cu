@@ -36,6 +36,12 @@ struct GemmTcParams {
     int64_t total_tiles;
     int is_bf16;
     int a_bmul, b_bmul;  // 0 when the operand is broadcast over the batch
+    // fused epilogues (README.md:32): out = alpha * acc + beta * C + residual
+    const void *residual;  // same dtype as C, or null
+    int64_t ldr, sr;
+    // GLU (CTA-pair kernel only): the accumulator holds u = A B1 in columns [0, 128) and v = A B3 in [128, 256); out = u o v,
+    // u / v optionally stored for the backward pass
+    void *glu_u, *glu_v;
 };
 
 template <int BN>
@@ -65,7 +71,8 @@ __device__ __forceinline__ void tile_coords(int64_t t, const GemmTcParams &p, in
 
 // One epilogue thread = one accumulator row: TMEM -> registers (32 fp32 columns at a time) -> alpha/beta -> 16-bit pack -> 16-byte stores
 template <int BN>
-__device__ __forceinline__ void epilogue_tile(const GemmTcParams &p, uint32_t taddr, int64_t row, int64_t n0, uint16_t *crow, bool vec_ok) {
+__device__ __forceinline__ void epilogue_tile(const GemmTcParams &p, uint32_t taddr, int64_t row, int64_t n0, uint16_t *crow, const uint16_t *rrow,
+                                              bool vec_ok) {
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
         uint32_t r[32];
@@ -83,6 +90,38 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams &p, uint32_t ta
                         const uint16_t old = crow[n0 + c + i];
                         const float o = p.is_bf16 ? __bfloat162float(__ushort_as_bfloat16(old)) : __half2float(__ushort_as_half(old));
                         v[i] += p.beta * o;
+                    }
+                }
+            }
+            if (rrow != nullptr) {  // + residual (x + gemm(...)): one pass instead of a GEMM store + an elementwise add
+                uint32_t rw[16];
+                if (full_chunk && vec_ok) {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(rrow + n0 + c);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint4 q = __ldg(src + i);
+                        rw[4 * i] = q.x; rw[4 * i + 1] = q.y; rw[4 * i + 2] = q.z; rw[4 * i + 3] = q.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const uint32_t lo = (n0 + c + 2 * i < p.N) ? rrow[n0 + c + 2 * i] : 0u, hi = (n0 + c + 2 * i + 1 < p.N) ? rrow[n0 + c + 2 * i + 1] : 0u;
+                        rw[i] = lo | (hi << 16);
+                    }
+                }
+                // the unfused form rounds the product to 16 bits before the add: do the same so that both paths agree bit for bit
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    if (p.is_bf16) {
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                        const float2 g = __bfloat1622float2(h), r2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rw[i]));
+                        v[2 * i] = r2.x + g.x;
+                        v[2 * i + 1] = r2.y + g.y;
+                    } else {
+                        const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                        const float2 g = __half22float2(h), r2 = __half22float2(*reinterpret_cast<const __half2 *>(&rw[i]));
+                        v[2 * i] = r2.x + g.x;
+                        v[2 * i + 1] = r2.y + g.y;
                     }
                 }
             }
@@ -107,6 +146,58 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams &p, uint32_t ta
                     if (n0 + c + i < p.N) crow[n0 + c + i] = (uint16_t)((packed[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
                 }
             }
+        }
+    }
+}
+
+// GLU epilogue: accumulator columns [c, c+32) hold u, [HN + c, HN + c + 32) hold v.  u and v are rounded to 16 bits first and the
+// product is formed from the rounded values, exactly what gemm(), gemm() and `*` produce when they run as three launches.
+template <int HN>
+__device__ __forceinline__ void epilogue_tile_glu(const GemmTcParams &p, uint32_t taddr, int64_t row, int64_t n0, uint16_t *crow, uint16_t *urow,
+                                                  uint16_t *vrow, bool vec_ok) {
+#pragma unroll 1
+    for (int c = 0; c < HN; c += 32) {
+        uint32_t ru[32], rv[32];
+        tmem_ld32(taddr + (uint32_t)c, ru);
+        tmem_ld32(taddr + (uint32_t)(HN + c), rv);
+        tmem_ld_wait();
+        if (row < p.M && n0 + c < p.N) {
+            uint32_t pu[16], pv[16], ph[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float u0 = __uint_as_float(ru[2 * i]) * p.alpha, u1 = __uint_as_float(ru[2 * i + 1]) * p.alpha;
+                const float v0 = __uint_as_float(rv[2 * i]) * p.alpha, v1 = __uint_as_float(rv[2 * i + 1]) * p.alpha;
+                if (p.is_bf16) {
+                    const __nv_bfloat162 hu = __floats2bfloat162_rn(u0, u1), hv = __floats2bfloat162_rn(v0, v1);
+                    const float2 fu = __bfloat1622float2(hu), fv = __bfloat1622float2(hv);
+                    const __nv_bfloat162 hh = __floats2bfloat162_rn(fu.x * fv.x, fu.y * fv.y);
+                    pu[i] = *reinterpret_cast<const uint32_t *>(&hu);
+                    pv[i] = *reinterpret_cast<const uint32_t *>(&hv);
+                    ph[i] = *reinterpret_cast<const uint32_t *>(&hh);
+                } else {
+                    const __half2 hu = __floats2half2_rn(u0, u1), hv = __floats2half2_rn(v0, v1);
+                    const float2 fu = __half22float2(hu), fv = __half22float2(hv);
+                    const __half2 hh = __floats2half2_rn(fu.x * fv.x, fu.y * fv.y);
+                    pu[i] = *reinterpret_cast<const uint32_t *>(&hu);
+                    pv[i] = *reinterpret_cast<const uint32_t *>(&hv);
+                    ph[i] = *reinterpret_cast<const uint32_t *>(&hh);
+                }
+            }
+            const bool full_chunk = n0 + c + 32 <= p.N;
+            auto put = [&](uint16_t *dst_row, const uint32_t (&w)[16]) {
+                if (full_chunk && vec_ok) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(dst_row + n0 + c);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (n0 + c + i < p.N) dst_row[n0 + c + i] = (uint16_t)((w[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
+                }
+            };
+            put(crow, ph);
+            if (urow) put(urow, pu);
+            if (vrow) put(vrow, pv);
         }
     }
 }
@@ -228,7 +319,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int q = warp & 3;
         int acc = 0;
         uint32_t acc_ph = 0;
-        const bool vec_ok = (p.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0) && (p.sc % 8 == 0);
+        const bool vec_ok = (p.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0) && (p.sc % 8 == 0) &&
+                            (!p.residual || ((p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) && (p.sr % 8 == 0)));
         for (int64_t t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             int b, mb, nb;
             tile_coords<16>(t, p, b, mb, nb);
@@ -238,7 +330,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             uint16_t *crow = reinterpret_cast<uint16_t *>(p.c) + (int64_t)b * p.sc + row * p.ldc;
-            epilogue_tile<BN>(p, taddr, row, n0, crow, vec_ok);
+            const uint16_t *rrow = p.residual ? reinterpret_cast<const uint16_t *>(p.residual) + (int64_t)b * p.sr + row * p.ldr : nullptr;
+            epilogue_tile<BN>(p, taddr, row, n0, crow, rrow, vec_ok);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -278,6 +371,7 @@ static void launch_tc_cfg(const GemmPlan &g) {
     p.is_bf16 = bf16;
     p.a_bmul = a_nb > 1 || g.batch == 1 ? 1 : 0;
     p.b_bmul = b_nb > 1 || g.batch == 1 ? 1 : 0;
+    p.residual = g.residual; p.ldr = g.ldr; p.sr = g.sr;
     auto kernel = gemm_tc_kernel<BN, A_MN, B_MN>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -309,9 +403,12 @@ struct GemmSmem2 {
     static constexpr int TOTAL = NSTAGES * STAGE_BYTES + BAR_BYTES + 1024;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+// GLU = true: rank 0 stages B1[:, n0 .. n0+128) and rank 1 stages B3[:, n0 .. n0+128) (tmap_b2), so ONE M256 N256 MMA stream
+// produces u = A B1 in accumulator columns [0, 128) and v = A B3 in [128, 256); the epilogue writes u o v (and u, v when asked).
+template <int BN, bool A_MN, bool B_MN, bool GLU>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmTcParams p) {
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b2,
+                const GemmTcParams p) {
     using S = GemmSmem2<BN>;
     constexpr int NST = S::NSTAGES;
     constexpr int HALF_N = BN / 2;
@@ -356,7 +453,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             for (int64_t t = cluster_id; t < p.total_tiles; t += n_clusters) {
                 int b, mb, nb;
                 tile_coords<8>(t, p, b, mb, nb);
-                const int m0 = mb * (2 * G_BM) + (int)rank * G_BM, n0 = nb * BN + (int)rank * HALF_N;
+                const int m0 = mb * (2 * G_BM) + (int)rank * G_BM, n0 = GLU ? nb * HALF_N : nb * BN + (int)rank * HALF_N;
+                const CUtensorMap *tmb = (GLU && rank == 1) ? &tmap_b2 : &tmap_b;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&empty[s], ph ^ 1);
                     unsigned char *sa = smem + s * S::STAGE_BYTES;
@@ -371,10 +469,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         for (int i = 0; i < G_BM / 64; ++i) tma_load_3d_2sm(sa + i * (64 * G_BK * 2), &tmap_a, fb, m0 + i * 64, k0, b * p.a_bmul);
                     }
                     if constexpr (!B_MN) {
-                        tma_load_3d_2sm(sb, &tmap_b, fb, k0, n0, b * p.b_bmul);  // box 64(k) x BN/2(n)
+                        tma_load_3d_2sm(sb, tmb, fb, k0, n0, b * p.b_bmul);  // box 64(k) x BN/2(n)
                     } else {
 #pragma unroll
-                        for (int i = 0; i < HALF_N / 64; ++i) tma_load_3d_2sm(sb + i * (64 * G_BK * 2), &tmap_b, fb, n0 + i * 64, k0, b * p.b_bmul);
+                        for (int i = 0; i < HALF_N / 64; ++i) tma_load_3d_2sm(sb + i * (64 * G_BK * 2), tmb, fb, n0 + i * 64, k0, b * p.b_bmul);
                     }
                     if (++s == NST) {
                         s = 0;
@@ -427,18 +525,27 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         const int q = warp & 3;
         int acc = 0;
         uint32_t acc_ph = 0;
-        const bool vec_ok = (p.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0) && (p.sc % 8 == 0);
+        const bool vec_ok = (p.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0) && (p.sc % 8 == 0) &&
+                            (!p.residual || ((p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) && (p.sr % 8 == 0))) &&
+                            (!p.glu_u || (((reinterpret_cast<uintptr_t>(p.glu_u) | reinterpret_cast<uintptr_t>(p.glu_v)) & 15) == 0));
         const uint32_t tmem_empty0 = mapa_u32(&tmem_empty[0], 0);
         for (int64_t t = cluster_id; t < p.total_tiles; t += n_clusters) {
             int b, mb, nb;
             tile_coords<8>(t, p, b, mb, nb);
             const int64_t row = (int64_t)mb * (2 * G_BM) + (int64_t)rank * G_BM + q * 32 + lane;
-            const int64_t n0 = (int64_t)nb * BN;
+            const int64_t n0 = (int64_t)nb * (GLU ? HALF_N : BN);
             mbar_wait_cluster(&tmem_full[acc], acc_ph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             uint16_t *crow = reinterpret_cast<uint16_t *>(p.c) + (int64_t)b * p.sc + row * p.ldc;
-            epilogue_tile<BN>(p, taddr, row, n0, crow, vec_ok);
+            if constexpr (GLU) {
+                const int64_t off = (int64_t)b * p.sc + row * p.ldc;
+                epilogue_tile_glu<HALF_N>(p, taddr, row, n0, crow, p.glu_u ? reinterpret_cast<uint16_t *>(p.glu_u) + off : nullptr,
+                                          p.glu_v ? reinterpret_cast<uint16_t *>(p.glu_v) + off : nullptr, vec_ok);
+            } else {
+                const uint16_t *rrow = p.residual ? reinterpret_cast<const uint16_t *>(p.residual) + (int64_t)b * p.sr + row * p.ldr : nullptr;
+                epilogue_tile<BN>(p, taddr, row, n0, crow, rrow, vec_ok);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tmem_empty0 + (uint32_t)acc * 8u);
@@ -457,7 +564,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool GLU = false>
 static void launch_tc2_cfg(const GemmPlan &g) {
     using S = GemmSmem2<BN>;
     Runtime &rt = Runtime::get();
@@ -467,25 +574,45 @@ static void launch_tc2_cfg(const GemmPlan &g) {
                                 : make_tmap_3d_16bit(g.a, bf16, (uint64_t)g.K, (uint64_t)g.M, a_nb, (uint64_t)g.lda, (uint64_t)g.sa, 64, G_BM);
     const CUtensorMap tb = B_MN ? make_tmap_3d_16bit(g.b, bf16, (uint64_t)g.N, (uint64_t)g.K, b_nb, (uint64_t)g.ldb, (uint64_t)g.sb, 64, 64)
                                 : make_tmap_3d_16bit(g.b, bf16, (uint64_t)g.K, (uint64_t)g.N, b_nb, (uint64_t)g.ldb, (uint64_t)g.sb, 64, BN / 2);
+    CUtensorMap tb2 = tb;
+    if (GLU)
+        tb2 = B_MN ? make_tmap_3d_16bit(g.b2, bf16, (uint64_t)g.N, (uint64_t)g.K, b_nb, (uint64_t)g.ldb, (uint64_t)g.sb, 64, 64)
+                   : make_tmap_3d_16bit(g.b2, bf16, (uint64_t)g.K, (uint64_t)g.N, b_nb, (uint64_t)g.ldb, (uint64_t)g.sb, 64, BN / 2);
     GemmTcParams p{};
     p.M = g.M; p.N = g.N; p.K = g.K; p.batch = g.batch;
     p.ldc = g.ldc; p.sc = g.sc; p.c = g.c;
     p.alpha = g.alpha; p.beta = g.beta;
+    p.residual = g.residual; p.ldr = g.ldr; p.sr = g.sr;
+    p.glu_u = g.glu_u; p.glu_v = g.glu_v;
     p.m_tiles = (int)((g.M + 2 * G_BM - 1) / (2 * G_BM));
-    p.n_tiles = (int)((g.N + BN - 1) / BN);
+    p.n_tiles = (int)((g.N + (GLU ? BN / 2 : BN) - 1) / (GLU ? BN / 2 : BN));
     p.total_tiles = (int64_t)p.m_tiles * p.n_tiles * g.batch;
     p.is_bf16 = bf16;
     p.a_bmul = a_nb > 1 || g.batch == 1 ? 1 : 0;
     p.b_bmul = b_nb > 1 || g.batch == 1 ? 1 : 0;
-    auto kernel = gemm_tc2_kernel<BN, A_MN, B_MN>;
+    auto kernel = gemm_tc2_kernel<BN, A_MN, B_MN, GLU>;
     static bool attr_done = false;
     if (!attr_done) {
         KF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
         attr_done = true;
     }
     const int64_t clusters = std::min<int64_t>(p.total_tiles, rt.props().sm_count / 2);
-    kernel<<<(unsigned)(2 * clusters), G_THREADS, S::TOTAL, rt.stream()>>>(ta, tb, p);
-    rt.post_launch("gemm_tc2_kernel");
+    kernel<<<(unsigned)(2 * clusters), G_THREADS, S::TOTAL, rt.stream()>>>(ta, tb, tb2, p);
+    rt.post_launch(GLU ? "gemm_tc2_glu_kernel" : "gemm_tc2_kernel");
+}
+
+// h = (A B1) o (A B3) in one launch (GLU feed-forward).  A [M,K] row-major, B1 / B3 [K,N] row-major (or both
+// transposed), same leading dimension.  false => caller composes it from two GEMMs and a multiply.
+bool launch_gemm_glu_tc(const GemmPlan &g) {
+    if (g.dtype != KF_HALF && g.dtype != KF_BFLOAT16) return false;
+    if (g.b2 == nullptr || g.batch != 1 || g.trans_a || g.beta != 0.f || g.residual) return false;
+    if (g.M <= 128 || g.N < 128 || g.K <= 0) return false;
+    auto aligned = [](const void *p, int64_t ld) { return (reinterpret_cast<uintptr_t>(p) % 16 == 0) && (ld % 8 == 0); };
+    if (!aligned(g.a, g.lda) || !aligned(g.b, g.ldb) || !aligned(g.b2, g.ldb)) return false;
+    if (g.M >= (1ll << 31) || g.N >= (1ll << 31) || g.K >= (1ll << 31)) return false;
+    if (g.trans_b) launch_tc2_cfg<256, false, false, true>(g);
+    else launch_tc2_cfg<256, false, true, true>(g);
+    return true;
 }
 
 bool launch_gemm_tc(const GemmPlan &g) {

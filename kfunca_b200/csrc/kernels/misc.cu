@@ -59,6 +59,107 @@ void launch_index_put(void *self, int dtype, const int64_t *self_shape, const in
     rt.post_launch("index_put_kernel");
 }
 
+// ---- embedding gather: out[i, :] = weight[idx[i], :]  (bit-exact row copy; negative ids wrap like index_put_, bad ids give zeros)
+template <typename V>
+__global__ void __launch_bounds__(256) embedding_fwd_kernel(const V *__restrict__ w, const int64_t *__restrict__ idx, V *__restrict__ out,
+                                                            const int64_t n, const int64_t Vrows, const int64_t row_vecs) {
+    const int64_t total = n * row_vecs;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / row_vecs, c = t % row_vecs;
+        int64_t ix = __ldg(idx + i);
+        if (ix < 0) ix += Vrows;
+        V v{};
+        if (ix >= 0 && ix < Vrows) v = __ldg(w + ix * row_vecs + c);
+        out[t] = v;
+    }
+}
+
+void launch_embedding_fwd(const void *weight, const int64_t *idx, void *out, int dtype, int64_t n, int64_t V, int64_t E) {
+    Runtime &rt = Runtime::get();
+    const int64_t row_bytes = E * (int64_t)element_size(dtype);
+    const bool v16 = row_bytes % 16 == 0 && reinterpret_cast<uintptr_t>(weight) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0;
+    if (v16) {
+        const int64_t rv = row_bytes / 16;
+        embedding_fwd_kernel<uint4><<<grid_for(n * rv, 256, 8), 256, 0, rt.stream()>>>((const uint4 *)weight, idx, (uint4 *)out, n, V, rv);
+    } else {
+        switch (element_size(dtype)) {
+        case 1: embedding_fwd_kernel<uint8_t><<<grid_for(n * E, 256, 8), 256, 0, rt.stream()>>>((const uint8_t *)weight, idx, (uint8_t *)out, n, V, E); break;
+        case 2: embedding_fwd_kernel<uint16_t><<<grid_for(n * E, 256, 8), 256, 0, rt.stream()>>>((const uint16_t *)weight, idx, (uint16_t *)out, n, V, E); break;
+        case 4: embedding_fwd_kernel<uint32_t><<<grid_for(n * E, 256, 8), 256, 0, rt.stream()>>>((const uint32_t *)weight, idx, (uint32_t *)out, n, V, E); break;
+        default: embedding_fwd_kernel<uint64_t><<<grid_for(n * E, 256, 8), 256, 0, rt.stream()>>>((const uint64_t *)weight, idx, (uint64_t *)out, n, V, E); break;
+        }
+    }
+    rt.post_launch("embedding_fwd_kernel");
+}
+
+// ---- embedding backward: dW[v, :] = sum over the positions p with idx[p] == v of grad[p, :], summed in ascending p.
+// `sorted_idx` / `sorted_pos` come from the library's stable sort of idx.  One warp per run start; lanes stride the columns.
+template <typename T, typename A>
+__global__ void __launch_bounds__(256) embedding_bwd_kernel(const T *__restrict__ grad, const int64_t *__restrict__ sidx, const int64_t *__restrict__ spos,
+                                                            T *__restrict__ dw, const int64_t n, const int64_t Vrows, const int64_t E) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < n; p += warps) {
+        const int64_t v = sidx[p];
+        if (p > 0 && sidx[p - 1] == v) continue;  // not the start of a run
+        int64_t row = v < 0 ? v + Vrows : v;
+        if (row < 0 || row >= Vrows) continue;
+        int64_t q_end = p + 1;
+        while (q_end < n && sidx[q_end] == v) ++q_end;
+        for (int64_t c = lane; c < E; c += 32) {
+            A acc = A(0);
+            for (int64_t q = p; q < q_end; ++q) acc += cvt_in<A>(grad[spos[q] * E + c]);
+            dw[row * E + c] = cvt_out<T, A>(acc);
+        }
+    }
+}
+
+void launch_embedding_bwd(const void *grad, const int64_t *sorted_idx, const int64_t *sorted_pos, void *dweight, int dtype, int64_t n, int64_t V,
+                          int64_t E) {
+    Runtime &rt = Runtime::get();
+    const int grid = grid_for(n * 32, 256, 8);
+    switch (dtype) {
+    case KF_FLOAT: embedding_bwd_kernel<float, float><<<grid, 256, 0, rt.stream()>>>((const float *)grad, sorted_idx, sorted_pos, (float *)dweight, n, V, E); break;
+    case KF_DOUBLE: embedding_bwd_kernel<double, double><<<grid, 256, 0, rt.stream()>>>((const double *)grad, sorted_idx, sorted_pos, (double *)dweight, n, V, E); break;
+    case KF_HALF: embedding_bwd_kernel<__half, float><<<grid, 256, 0, rt.stream()>>>((const __half *)grad, sorted_idx, sorted_pos, (__half *)dweight, n, V, E); break;
+    case KF_BFLOAT16:
+        embedding_bwd_kernel<__nv_bfloat16, float><<<grid, 256, 0, rt.stream()>>>((const __nv_bfloat16 *)grad, sorted_idx, sorted_pos, (__nv_bfloat16 *)dweight, n, V, E);
+        break;
+    default: KF_CHECK(false, "embedding backward: floating dtypes only");
+    }
+    rt.post_launch("embedding_bwd_kernel");
+}
+
+// ---- counter-based uniform fill (test / bench input generator; host twin: oracle.counter_uniform)
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {  // splitmix64 finaliser
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+template <typename T>
+__global__ void __launch_bounds__(256) fill_random_kernel(T *__restrict__ p, const int64_t n, const uint64_t seed, const float lo, const float span) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t h = mix64((uint64_t)i + seed * 0x9E3779B97F4A7C15ull);
+        const float u = (float)(uint32_t)(h >> 40) * 5.9604644775390625e-8f;  // 24 random bits -> [0, 1), exact in fp32
+        p[i] = cvt_out<T, float>(__fadd_rn(lo, __fmul_rn(span, u)));
+    }
+}
+template <> __device__ __forceinline__ double cvt_out<double, float>(float x) { return (double)x; }
+
+void launch_fill_random(void *p, int dtype, int64_t n, uint64_t seed, float lo, float hi) {
+    Runtime &rt = Runtime::get();
+    const int grid = grid_for(n, 256, 16);
+    const float span = hi - lo;
+    switch (dtype) {
+    case KF_FLOAT: fill_random_kernel<float><<<grid, 256, 0, rt.stream()>>>((float *)p, n, seed, lo, span); break;
+    case KF_DOUBLE: fill_random_kernel<double><<<grid, 256, 0, rt.stream()>>>((double *)p, n, seed, lo, span); break;
+    case KF_HALF: fill_random_kernel<__half><<<grid, 256, 0, rt.stream()>>>((__half *)p, n, seed, lo, span); break;
+    case KF_BFLOAT16: fill_random_kernel<__nv_bfloat16><<<grid, 256, 0, rt.stream()>>>((__nv_bfloat16 *)p, n, seed, lo, span); break;
+    default: KF_CHECK(false, "random fill: floating dtypes only");
+    }
+    rt.post_launch("fill_random_kernel");
+}
+
 std::string device_info_string() {
     Runtime &rt = Runtime::get();
     const DeviceProps &p = rt.props();

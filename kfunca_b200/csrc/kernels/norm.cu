@@ -14,9 +14,12 @@
 //   backward: dx with one row per CTA; the gain gradient in a second launch of persistent CTAs that stride over the rows, each
 //             thread keeping the partial sums of ITS columns in registers, written once to a [CTAs, E] fp32 scratch that the
 //             ordinary column reduction folds afterwards: deterministic, no atomics.
+#include <cooperative_groups.h>
+
 #include "ew_common.cuh"
 
 namespace kf {
+namespace cg = cooperative_groups;
 
 constexpr int LN_THREADS = 128;
 
@@ -45,6 +48,7 @@ struct LnArgs {
     float *dgain_partial;    // [gridDim.x, E] (backward)
     int64_t rows, E;
     float eps;
+    int rms;                 // 1 = RMSNorm (README.md:28 `rms_norm`): no centring, rstd = 1 / sqrt(mean(x^2) + eps), mean stored as 0
 };
 
 template <typename T, int VEC, int NV>
@@ -67,7 +71,7 @@ __global__ void __launch_bounds__(LN_THREADS) layer_norm_fwd_kernel(const LnArgs
             }
         }
     }
-    const float mean = ln_block_sum(s, red) / (float)a.E;
+    const float mean = a.rms ? 0.f : ln_block_sum(s, red) / (float)a.E;  // a.rms is uniform over the grid: no divergent barrier
     float d = 0.f;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(LN_THREADS) layer_norm_bwd_kernel(const LnArgs
                 slot[4 + (threadIdx.x >> 5)] = s2;
             }
             __syncthreads();
-            const float c1 = ((slot[0] + slot[1]) + (slot[2] + slot[3])) / (float)a.E;
+            const float c1 = a.rms ? 0.f : ((slot[0] + slot[1]) + (slot[2] + slot[3])) / (float)a.E;
             const float c2 = ((slot[4] + slot[5]) + (slot[6] + slot[7])) / (float)a.E;
             T *__restrict__ dx = reinterpret_cast<T *>(a.dx) + row * a.E;
 #pragma unroll
@@ -259,10 +263,11 @@ static void ln_fwd_typed(const LnArgs &a) {
     rt.post_launch("layer_norm_fwd_kernel");
 }
 
-void launch_layer_norm_fwd(const void *x, const void *gain, void *y, float *mean, float *rstd, int dtype, int64_t rows, int64_t E, float eps) {
+void launch_layer_norm_fwd(const void *x, const void *gain, void *y, float *mean, float *rstd, int dtype, int64_t rows, int64_t E, float eps,
+                           bool rms) {
     if (rows == 0) return;
     LnArgs a{};
-    a.x = x; a.gain = gain; a.y = y; a.mean = mean; a.rstd = rstd; a.rows = rows; a.E = E; a.eps = eps;
+    a.x = x; a.gain = gain; a.y = y; a.mean = mean; a.rstd = rstd; a.rows = rows; a.E = E; a.eps = eps; a.rms = rms ? 1 : 0;
     if (dtype == KF_FLOAT) ln_fwd_typed<float>(a);
     else if (dtype == KF_HALF) ln_fwd_typed<__half>(a);
     else ln_fwd_typed<__nv_bfloat16>(a);
@@ -284,6 +289,183 @@ bool launch_row_moments(const void *x, void *mean, void *var, int dtype, int64_t
     default: row_moments_kernel<float, 4, 8><<<grid, LN_THREADS, 0, rt.stream()>>>(xp, mp, vp, E, take_sqrt); break;
     }
     rt.post_launch("row_moments_kernel");
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Column statistics in ONE launch: x viewed as [outer, R, inner], statistics over R for every (outer, inner) column.
+//   mode 0 (norm_stat, ref: norm_stat_kernel, src/device/norm_ops_kernel.cu:6-61 + WelfordNormPFKernel, welford_norm.h:25-355):
+//           out0 = mean, out1 = 1 / sqrt(M2 / R + eps)            (biased variance)
+//   mode 1 (mean_var over a non-last dim, ref: reduce_ops_kernel.cu:61-153, Welford with correction 1):
+//           out0 = mean, out1 = M2 / (R - 1)   [sqrt when take_sqrt]
+// A cluster of CM_C CTAs along R shares a 32 * VEC wide column strip; every thread runs Welford over its rows (one reciprocal per
+// row shared by its VEC columns), the 8 warps merge through shared memory (Chan's pairwise update, fixed order), the CTAs merge
+// through distributed shared memory in rank order: deterministic, no atomics, no staging buffer, no semaphore (the reference's
+// un-zeroed semaphore block, SURVEY F10, has no counterpart).
+constexpr int CM_C = 8, CM_WARPS = 8;
+
+struct ColMomentsArgs {
+    const float *x;
+    float *out0, *out1;
+    int64_t outer, R, inner;
+    float eps;
+    int mode, take_sqrt;
+};
+
+__device__ __forceinline__ void chan_merge(float &na, float &ma, float &sa, const float nb, const float mb, const float sb) {
+    const float n = na + nb;
+    if (nb == 0.f) return;
+    const float d = mb - ma, f = nb / n;
+    ma = fmaf(d, f, ma);
+    sa = sa + sb + d * d * na * f;
+    na = n;
+}
+
+template <int VEC>
+__global__ void __cluster_dims__(1, CM_C, 1) __launch_bounds__(CM_WARPS * 32) col_moments_kernel(const ColMomentsArgs a) {
+    __shared__ float w_mean[CM_WARPS][32 * VEC], w_m2[CM_WARPS][32 * VEC], w_n[CM_WARPS];
+    __shared__ float c_mean[32 * VEC], c_m2[32 * VEC], c_n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t o = blockIdx.z;
+    const int64_t col0 = ((int64_t)blockIdx.x * 32 + lane) * VEC;
+    const bool col_ok = col0 < a.inner;  // VEC > 1 only when inner % VEC == 0
+    const float *__restrict__ base = a.x + o * a.R * a.inner + col0;
+    float n = 0.f, mean[VEC], m2[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) mean[i] = m2[i] = 0.f;
+    const int64_t r0 = (int64_t)blockIdx.y * CM_WARPS + warp, rstep = (int64_t)CM_C * CM_WARPS;
+    if (col_ok) {
+        int64_t r = r0;
+        // two rows in flight per thread
+        for (; r + rstep < a.R; r += 2 * rstep) {
+            float v0[VEC], v1[VEC];
+            if (VEC == 4) {
+                const float4 f0 = __ldcs(reinterpret_cast<const float4 *>(base + r * a.inner));
+                const float4 f1 = __ldcs(reinterpret_cast<const float4 *>(base + (r + rstep) * a.inner));
+                v0[0] = f0.x; v0[VEC > 1 ? 1 : 0] = f0.y; v0[VEC > 2 ? 2 : 0] = f0.z; v0[VEC > 3 ? 3 : 0] = f0.w;
+                v1[0] = f1.x; v1[VEC > 1 ? 1 : 0] = f1.y; v1[VEC > 2 ? 2 : 0] = f1.z; v1[VEC > 3 ? 3 : 0] = f1.w;
+            } else {
+                v0[0] = __ldcs(base + r * a.inner);
+                v1[0] = __ldcs(base + (r + rstep) * a.inner);
+            }
+            n += 1.f;
+            float inv = __frcp_rn(n);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const float d = v0[i] - mean[i];
+                mean[i] = fmaf(d, inv, mean[i]);
+                m2[i] = fmaf(d, v0[i] - mean[i], m2[i]);
+            }
+            n += 1.f;
+            inv = __frcp_rn(n);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const float d = v1[i] - mean[i];
+                mean[i] = fmaf(d, inv, mean[i]);
+                m2[i] = fmaf(d, v1[i] - mean[i], m2[i]);
+            }
+        }
+        for (; r < a.R; r += rstep) {
+            float v0[VEC];
+            if (VEC == 4) {
+                const float4 f0 = __ldcs(reinterpret_cast<const float4 *>(base + r * a.inner));
+                v0[0] = f0.x; v0[VEC > 1 ? 1 : 0] = f0.y; v0[VEC > 2 ? 2 : 0] = f0.z; v0[VEC > 3 ? 3 : 0] = f0.w;
+            } else {
+                v0[0] = __ldcs(base + r * a.inner);
+            }
+            n += 1.f;
+            const float inv = __frcp_rn(n);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const float d = v0[i] - mean[i];
+                mean[i] = fmaf(d, inv, mean[i]);
+                m2[i] = fmaf(d, v0[i] - mean[i], m2[i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        w_mean[warp][lane * VEC + i] = mean[i];
+        w_m2[warp][lane * VEC + i] = m2[i];
+    }
+    // the row count of a warp does not depend on the column: lanes without a valid column report the count too (uniform merge)
+    if (lane == 0) w_n[warp] = r0 < a.R ? (float)((a.R - r0 + rstep - 1) / rstep) : 0.f;
+    __syncthreads();
+    if (warp == 0) {
+        float cn = w_n[0];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            mean[i] = w_mean[0][lane * VEC + i];
+            m2[i] = w_m2[0][lane * VEC + i];
+        }
+        for (int w = 1; w < CM_WARPS; ++w) {
+            const float nb = w_n[w];
+            float nn = cn;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                nn = cn;
+                chan_merge(nn, mean[i], m2[i], nb, w_mean[w][lane * VEC + i], w_m2[w][lane * VEC + i]);
+            }
+            cn = nb == 0.f ? cn : nn;
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            c_mean[lane * VEC + i] = mean[i];
+            c_m2[lane * VEC + i] = m2[i];
+        }
+        if (lane == 0) c_n = cn;
+    }
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();
+    if (cluster.block_rank() == 0 && warp == 0) {
+        float cn = c_n;
+        for (unsigned rk = 1; rk < CM_C; ++rk) {
+            const float nb = *cluster.map_shared_rank(&c_n, rk);
+            const float *pm = cluster.map_shared_rank(&c_mean[0], rk), *ps = cluster.map_shared_rank(&c_m2[0], rk);
+            float nn = cn;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                nn = cn;
+                chan_merge(nn, mean[i], m2[i], nb, pm[lane * VEC + i], ps[lane * VEC + i]);
+            }
+            cn = nb == 0.f ? cn : nn;
+        }
+        if (col_ok) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                float second;
+                if (a.mode == 0) {
+                    second = rsqrtf(m2[i] / (float)a.R + a.eps);
+                } else {
+                    const float div = (float)a.R - 1.f;
+                    second = m2[i] / (div > 0.f ? div : 0.f);
+                    if (a.take_sqrt) second = sqrtf(second);
+                }
+                a.out0[o * a.inner + col0 + i] = mean[i];
+                a.out1[o * a.inner + col0 + i] = second;
+            }
+        }
+    }
+    cluster.sync();  // peers keep their shared memory alive until rank 0 has read it
+}
+
+bool launch_col_moments(const void *x, void *out0, void *out1, int dtype, int64_t outer, int64_t R, int64_t inner, int mode, bool take_sqrt,
+                        double eps) {
+    if (dtype != KF_FLOAT || R < 1 || inner < 1 || outer < 1 || outer > 65535) return false;
+    Runtime &rt = Runtime::get();
+    ColMomentsArgs a{};
+    a.x = reinterpret_cast<const float *>(x);
+    a.out0 = reinterpret_cast<float *>(out0);
+    a.out1 = reinterpret_cast<float *>(out1);
+    a.outer = outer; a.R = R; a.inner = inner;
+    a.eps = (float)eps; a.mode = mode; a.take_sqrt = take_sqrt ? 1 : 0;
+    const bool vec4 = inner % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0;
+    const int64_t strips = (inner + (vec4 ? 128 : 32) - 1) / (vec4 ? 128 : 32);
+    KF_CHECK(strips < (int64_t)0x7FFFFFFF);
+    const dim3 grid((unsigned)strips, CM_C, (unsigned)outer);
+    if (vec4) col_moments_kernel<4><<<grid, CM_WARPS * 32, 0, rt.stream()>>>(a);
+    else col_moments_kernel<1><<<grid, CM_WARPS * 32, 0, rt.stream()>>>(a);
+    rt.post_launch("col_moments_kernel");
     return true;
 }
 
@@ -317,9 +499,10 @@ static void ln_bwd_typed(const LnArgs &a, int ctas, bool write_dx) {
 
 // dx may be null (input needs no gradient); dgain_partial is [layer_norm_bwd_ctas(rows), E] fp32
 void launch_layer_norm_bwd(const void *x, const void *gain, const void *dy, const float *mean, const float *rstd, void *dx,
-                           float *dgain_partial, int ctas, int dtype, int64_t rows, int64_t E) {
+                           float *dgain_partial, int ctas, int dtype, int64_t rows, int64_t E, bool rms) {
     if (rows == 0) return;
     LnArgs a{};
+    a.rms = rms ? 1 : 0;
     a.x = x; a.gain = gain; a.dy = dy; a.dx = dx; a.mean = const_cast<float *>(mean); a.rstd = const_cast<float *>(rstd);
     a.dgain_partial = dgain_partial; a.rows = rows; a.E = E;
     if (dtype == KF_FLOAT) ln_bwd_typed<float>(a, ctas, dx != nullptr);

@@ -342,6 +342,16 @@ std::tuple<Tensor, Tensor> mean_var(const Tensor &self, int64_t dim, bool take_s
         Tensor m = empty(oshape, x.dtype(), x.device()), v = empty(oshape, x.dtype(), x.device());
         if (launch_row_moments(x.data(), m.data(), v.data(), x.dtype(), x.numel() / x.size(d), x.size(d), take_sqrt)) return {m, v};
     }
+    if (d != self.dim() - 1 && x.dtype() == KF_FLOAT && x.device() >= 0 && x.numel() > 0) {  // one-launch column statistics (kernels/norm.cu)
+        Tensor xc = x.is_contiguous() ? x : clone(x);
+        int64_t outer = 1, inner = 1;
+        for (int i = 0; i < d; ++i) outer *= xc.size(i);
+        for (int i = d + 1; i < xc.dim(); ++i) inner *= xc.size(i);
+        auto oshape = xc.sizes();
+        oshape[d] = 1;
+        Tensor m = empty(oshape, KF_FLOAT, xc.device()), v = empty(oshape, KF_FLOAT, xc.device());
+        if (launch_col_moments(xc.data(), m.data(), v.data(), KF_FLOAT, outer, xc.size(d), inner, 1, take_sqrt, 0.0)) return {m, v};
+    }
     Tensor m = mean(x, d);
     Tensor diff = binary(EW_SUB, x, m);
     Tensor m2 = sum(binary(EW_MUL, diff, diff), d);
@@ -357,6 +367,11 @@ std::tuple<Tensor, Tensor> norm_stat(const Tensor &self, int64_t dim) {
     KF_CHECK(dim == 0 && self.dim() == 2);
     KF_CHECK(self.dtype() == KF_FLOAT || self.dtype() == KF_DOUBLE, "Unsupported ScalarType ", dtype_name(self.dtype()));
     Tensor x = self.detach();
+    if (x.dtype() == KF_FLOAT && x.device() >= 0 && x.numel() > 0) {  // ONE launch (the reference: WelfordNormPFKernel + semaphores)
+        Tensor xc = x.is_contiguous() ? x : clone(x);
+        Tensor m = empty({1, xc.size(1)}, KF_FLOAT, xc.device()), is = empty({1, xc.size(1)}, KF_FLOAT, xc.device());
+        if (launch_col_moments(xc.data(), m.data(), is.data(), KF_FLOAT, 1, xc.size(0), xc.size(1), 0, false, 1e-12)) return {m, is};
+    }
     Tensor m = mean(x, 0);
     Tensor diff = binary(EW_SUB, x, m);
     Tensor var = mean(binary(EW_MUL, diff, diff), 0);
@@ -368,23 +383,30 @@ std::tuple<Tensor, Tensor> norm_stat(const Tensor &self, int64_t dim) {
 struct LayerNormGrad : GradFunction {
     Tensor x, gain, stats;  // stats: fp32 [2, rows] = mean | rstd
     int64_t rows, E;
+    bool rms = false;
     const char *name() const override { return "LayerNormGrad"; }
     std::vector<Tensor> backward(const Tensor &g0) override {
         Tensor g = g0.is_contiguous() ? g0 : clone(g0.detach());
+        if (reinterpret_cast<uintptr_t>(g.data()) % 16 != 0) g = clone(g.detach());  // the kernels use 16-byte vector loads
         const bool need_dx = inputs[0].requires_grad();
         Tensor dx;
         if (need_dx) dx = empty(x.sizes(), x.dtype(), x.device());
         const int ctas = layer_norm_bwd_ctas(rows);
-        Tensor partial = empty({(int64_t)ctas, E}, KF_FLOAT, x.device());
+        Tensor partial = rows > 0 ? empty({(int64_t)ctas, E}, KF_FLOAT, x.device()) : zeros({(int64_t)ctas, E}, KF_FLOAT, x.device());
         const float *st = reinterpret_cast<const float *>(stats.data());
         launch_layer_norm_bwd(x.data(), gain.data(), g.data(), st, st + rows, need_dx ? dx.data() : nullptr,
-                              reinterpret_cast<float *>(partial.data()), ctas, x.dtype(), rows, E);
+                              reinterpret_cast<float *>(partial.data()), ctas, x.dtype(), rows, E, rms);
         Tensor dgain = convert(sum(partial, 0), x.dtype()).view(gain.sizes());
         return {dx, dgain};
     }
 };
 
-Tensor layer_norm(const Tensor &x_, const Tensor &gain_, double eps) {
+static Tensor norm_impl(const Tensor &x_, const Tensor &gain_, double eps, bool rms);
+Tensor layer_norm(const Tensor &x, const Tensor &gain, double eps) { return norm_impl(x, gain, eps, false); }
+// y = x / sqrt(mean(x^2) + eps) * gain — the op the reference's README names as its next one (README.md:28 `rms_norm`)
+Tensor rms_norm(const Tensor &x, const Tensor &gain, double eps) { return norm_impl(x, gain, eps, true); }
+
+static Tensor norm_impl(const Tensor &x_, const Tensor &gain_, double eps, bool rms) {
     require_device(x_, "layer_norm");
     require_device(gain_, "layer_norm");
     KF_CHECK(x_.dim() >= 1 && x_.dtype() == gain_.dtype(), "layer_norm: x and gain must share a dtype");
@@ -396,8 +418,7 @@ Tensor layer_norm(const Tensor &x_, const Tensor &gain_, double eps) {
         // composed form (same arithmetic, several passes): rows too long for the register-resident kernels, or fp64
         std::vector<int64_t> gshape(x.dim(), 1);
         gshape.back() = E;
-        Tensor mu = mean(x, -1);
-        Tensor xc = binary(EW_SUB, x, mu);
+        Tensor xc = rms ? x : binary(EW_SUB, x, mean(x, -1));
         Tensor var = mean(binary(EW_MUL, xc, xc), -1);
         Tensor rstd = unary(EW_RSQRT, binary_scalar(EW_ADD, var, eps));
         return binary(EW_MUL, binary(EW_MUL, xc, rstd), view(gain, gshape));
@@ -406,7 +427,7 @@ Tensor layer_norm(const Tensor &x_, const Tensor &gain_, double eps) {
     Tensor out = empty(x.sizes(), x.dtype(), x.device());
     Tensor stats = empty({2, rows}, KF_FLOAT, x.device());
     float *st = reinterpret_cast<float *>(stats.data());
-    launch_layer_norm_fwd(x.data(), gain.data(), out.data(), st, st + rows, x.dtype(), rows, E, (float)eps);
+    launch_layer_norm_fwd(x.data(), gain.data(), out.data(), st, st + rows, x.dtype(), rows, E, (float)eps, rms);
     if (any_requires_grad({&x, &gain})) {
         auto *fn = new LayerNormGrad();
         fn->x = x.detach();
@@ -414,6 +435,7 @@ Tensor layer_norm(const Tensor &x_, const Tensor &gain_, double eps) {
         fn->stats = stats;
         fn->rows = rows;
         fn->E = E;
+        fn->rms = rms;
         attach(out, fn, {x, gain});
     }
     return out;
@@ -553,6 +575,41 @@ Tensor slice(const Tensor &self, int64_t dim, int64_t start, int64_t end, int64_
     return out;
 }
 
+Tensor narrow(const Tensor &self, int64_t dim, int64_t start, int64_t length) {
+    Tensor out = self.narrow(dim, start, length);  // bounds-checked view (ref: Tensor::narrow, tensor.cpp:233-244)
+    if (self.requires_grad()) {
+        const int d = wrap_dim(dim, self.dim());
+        auto *fn = new SliceGrad();
+        fn->in_shape = self.sizes();
+        fn->dim = d; fn->start = start; fn->end = start + length; fn->step = 1;
+        attach(out, fn, {self});
+    }
+    return out;
+}
+
+struct SelectGrad : GradFunction {  // x[i] along one dim: the gradient is scattered into a zero tensor of x's shape
+    std::vector<int64_t> in_shape;
+    int64_t dim, index;
+    const char *name() const override { return "SelectGrad"; }
+    std::vector<Tensor> backward(const Tensor &g) override {
+        Tensor gi = zeros(in_shape, g.dtype(), g.device());
+        Tensor dst = gi.select(dim, index);
+        run_copy(dst, g);
+        return {gi};
+    }
+};
+Tensor select(const Tensor &self, int64_t dim, int64_t index) {
+    Tensor out = self.select(dim, index);
+    if (self.requires_grad()) {
+        auto *fn = new SelectGrad();
+        fn->in_shape = self.sizes();
+        fn->dim = dim;
+        fn->index = index;
+        attach(out, fn, {self});
+    }
+    return out;
+}
+
 std::vector<Tensor> split(const Tensor &self, const std::vector<int64_t> &sizes, int64_t dim_) {
     KF_CHECK(self.dim() > 0, "tensor_split expected at least a 1-dimensional tensor, but got a tensor with ", self.dim(), " dims");
     const int d = wrap_dim(dim_, self.dim());
@@ -617,6 +674,55 @@ Tensor &index_put_(Tensor &self, const std::vector<Tensor> &indices, const Tenso
     return self;
 }
 
+// ---- embedding (ref: the gather half of IndexElementwiseKernel, src/device/utils/tensor_index.h:19-143,
+// src/core/index_ops.cpp:6-38; README.md:30 lists `embedding` as the reference's next op)
+struct EmbeddingGrad : GradFunction {
+    Tensor idx;  // int64, contiguous
+    int64_t V, E;
+    const char *name() const override { return "EmbeddingGrad"; }
+    std::vector<Tensor> backward(const Tensor &g0) override {
+        // deterministic scatter-add: stable-sort the token ids (ties keep ascending position), then every run of equal ids is
+        // summed in position order by ONE warp in fp32 — no atomics, bit-reproducible
+        Tensor g = g0.is_contiguous() ? g0 : clone(g0.detach());
+        const int64_t n = idx.numel();
+        Tensor dw = zeros({V, E}, g.dtype(), g.device());
+        if (n == 0) return {dw, Tensor()};
+        Tensor sv = empty({1, n}, KF_LONG, g.device()), si = empty({1, n}, KF_LONG, g.device());
+        launch_sort_rows(idx.data(), sv.data(), si.data_as<int64_t>(), KF_LONG, 1, n, false);
+        launch_embedding_bwd(g.data(), sv.data_as<int64_t>(), si.data_as<int64_t>(), dw.data(), g.dtype(), n, V, E);
+        return {dw, Tensor()};
+    }
+};
+
+Tensor embedding(const Tensor &weight, const Tensor &indices) {
+    require_device(weight, "embedding");
+    require_device(indices, "embedding");
+    KF_CHECK(weight.dim() == 2, "embedding: weight must be [V, E]");
+    KF_CHECK(indices.dtype() == KF_LONG, "Indices must be of type Long.");
+    Tensor w = weight.is_contiguous() ? weight : contiguous(weight);
+    Tensor idx = indices.detach().contiguous();
+    auto oshape = idx.sizes();
+    oshape.push_back(w.size(1));
+    Tensor out = empty(oshape, w.dtype(), w.device());
+    if (out.numel() > 0) launch_embedding_fwd(w.data(), idx.data_as<int64_t>(), out.data(), w.dtype(), idx.numel(), w.size(0), w.size(1));
+    if (weight.requires_grad()) {
+        auto *fn = new EmbeddingGrad();
+        fn->idx = idx;
+        fn->V = w.size(0);
+        fn->E = w.size(1);
+        attach(out, fn, {weight});
+    }
+    return out;
+}
+
+Tensor &random_uniform_(Tensor &self, uint64_t seed, double lo, double hi) {
+    require_device(self, "random_uniform_");
+    KF_CHECK(self.is_contiguous(), "random_uniform_: contiguous tensors only");
+    KF_CHECK(is_floating(self.dtype()), "random_uniform_: floating dtypes only");
+    if (self.numel() > 0) launch_fill_random(self.data(), self.dtype(), self.numel(), seed, (float)lo, (float)hi);
+    return self;
+}
+
 // ================================================================== GEMM
 static void fill_gemm_operand(const Tensor &t, bool trans, int64_t &rows, int64_t &cols, int64_t &ld, int64_t &bstride, int64_t &batch,
                               Tensor &holder) {
@@ -658,7 +764,8 @@ struct MatmulGrad : GradFunction {
     std::vector<Tensor> backward(const Tensor &g) override;
 };
 
-static Tensor matmul_nograd(const Tensor &a, bool ta, const Tensor &b, bool tb, float alpha, float beta, Tensor *out_opt) {
+static Tensor matmul_nograd(const Tensor &a, bool ta, const Tensor &b, bool tb, float alpha, float beta, Tensor *out_opt,
+                            const Tensor *residual = nullptr) {
     require_device(a, "matmul");
     require_device(b, "matmul");
     KF_CHECK(a.dtype() == b.dtype(), "matmul: dtype mismatch");
@@ -706,6 +813,14 @@ static Tensor matmul_nograd(const Tensor &a, bool ta, const Tensor &b, bool tb, 
     p.trans_b = tb;
     p.alpha = alpha;
     p.beta = beta;
+    Tensor rh;
+    if (residual) {
+        KF_CHECK(residual->dtype() == a.dtype() && residual->numel() == out.numel(), "gemm_residual: residual must match the output");
+        rh = residual->is_contiguous() ? *residual : clone(residual->detach());
+        p.residual = rh.data();
+        p.ldr = p.N;
+        p.sr = p.M * p.N;
+    }
     if (out.numel() > 0) launch_gemm(p);
     return out;
 }
@@ -719,14 +834,23 @@ std::vector<Tensor> MatmulGrad::backward(const Tensor &g0) {
         g2 = g.view({-1, g.size(-1)});
         a2 = a.contiguous().view({-1, a.size(-1)});
     }
+    // an operand whose batch was broadcast (batch 1 against a batched partner) gets the SUM of the per-batch gradients
+    auto fold_batch = [](const Tensor &grad, const Tensor &operand) {
+        if (grad.numel() == operand.numel()) return grad.sizes() == operand.sizes() ? grad : grad.contiguous().view(operand.sizes());
+        Tensor g3 = grad.contiguous().view({-1, grad.size(-2), grad.size(-1)});
+        KF_CHECK(g3.size(1) * g3.size(2) == operand.numel(), "MatmulGrad: gradient shape does not match a broadcast operand");
+        return sum(g3, 0).view(operand.sizes());
+    };
+    // dW (the operand the data-parallel all-reduce is waiting for) is issued BEFORE dX so that its collective can start one
+    // GEMM earlier under the overlapped schedule (kf_set_leaf_grad_hook)
+    if (nb) {
+        Tensor db = tb ? matmul_nograd(g2, true, a2, ta, alpha, 0.f, nullptr) : matmul_nograd(a2, !ta, g2, false, alpha, 0.f, nullptr);
+        r[1] = fold_batch(db, b);
+    }
     if (na) {
         // C = op(A) op(B): dA = dC op(B)^T (or its transpose when A was transposed)
         Tensor da = ta ? matmul_nograd(b, tb, g2, true, alpha, 0.f, nullptr) : matmul_nograd(g2, false, b, !tb, alpha, 0.f, nullptr);
-        r[0] = b_shared ? da.view(a.sizes()) : da;
-    }
-    if (nb) {
-        Tensor db = tb ? matmul_nograd(g2, true, a2, ta, alpha, 0.f, nullptr) : matmul_nograd(a2, !ta, g2, false, alpha, 0.f, nullptr);
-        r[1] = db;
+        r[0] = b_shared ? da.view(a.sizes()) : fold_batch(da, a);
     }
     return r;
 }
@@ -742,6 +866,96 @@ Tensor matmul(const Tensor &a, bool ta, const Tensor &b, bool tb, float alpha) {
         fn->alpha = alpha;
         fn->b_shared = (b.dim() == 2 && !ta && a.dim() > 2);
         attach(out, fn, {a, b});
+    }
+    return out;
+}
+
+// ---- fused GEMM epilogues (the reference lists the fused linear ops as its next ones, README.md:32)
+struct MatmulResidualGrad : MatmulGrad {  // inputs: a, b, residual
+    const char *name() const override { return "MatmulResidualGrad"; }
+    std::vector<Tensor> backward(const Tensor &g) override {
+        std::vector<Tensor> r = MatmulGrad::backward(g);
+        r.push_back(g);
+        return r;
+    }
+};
+
+// out = alpha * a @ b + residual in ONE kernel (the residual add runs in the GEMM epilogue); bit-identical to gemm() followed by +
+Tensor gemm_residual(const Tensor &a, const Tensor &b, const Tensor &residual, float alpha) {
+    KF_CHECK(a.is_contiguous() && b.is_contiguous(), "gemm: operands must be contiguous");
+    KF_CHECK(b.dim() == 2 && a.dim() >= 2 && b.size(0) == a.size(-1), "gemm: b must be [K, N]");
+    KF_CHECK(a.dtype() == b.dtype() && a.dtype() == residual.dtype(), "gemm: dtype mismatch");
+    auto oshape = a.sizes();
+    oshape.back() = b.size(1);
+    KF_CHECK(residual.sizes() == oshape, "gemm_residual: residual must have the shape of the result");
+    Tensor out = matmul_nograd(a, false, b, false, alpha, 0.f, nullptr, &residual);
+    if (any_requires_grad({&a, &b, &residual})) {
+        auto *fn = new MatmulResidualGrad();
+        fn->a = a.detach();
+        fn->b = b.detach();
+        fn->ta = false;
+        fn->tb = false;
+        fn->alpha = alpha;
+        fn->b_shared = a.dim() > 2;
+        attach(out, fn, {a, b, residual});
+    }
+    return out;
+}
+
+struct GluGrad : GradFunction {  // h = (a b1) o (a b3); inputs: a, b1, b3
+    Tensor a, b1, b3, u, v;
+    const char *name() const override { return "GluGrad"; }
+    std::vector<Tensor> backward(const Tensor &g0) override {
+        Tensor g = g0.contiguous();
+        Tensor du = binary(EW_MUL, g, v), dv = binary(EW_MUL, g, u);
+        Tensor a2 = a.view({-1, a.size(-1)}), du2 = du.view({-1, du.size(-1)}), dv2 = dv.view({-1, dv.size(-1)});
+        std::vector<Tensor> r(3);
+        if (inputs[1].requires_grad()) r[1] = matmul_nograd(a2, true, du2, false, 1.f, 0.f, nullptr);
+        if (inputs[2].requires_grad()) r[2] = matmul_nograd(a2, true, dv2, false, 1.f, 0.f, nullptr);
+        if (inputs[0].requires_grad()) {
+            // da = du b1^T + dv b3^T: the second product accumulates into the first through beta = 1 (no separate add)
+            Tensor da = matmul_nograd(du2, false, b1, true, 1.f, 0.f, nullptr);
+            matmul_nograd(dv2, false, b3, true, 1.f, 1.f, &da);
+            r[0] = da.view(a.sizes());
+        }
+        return r;
+    }
+};
+
+// h = gemm(a, b1) * gemm(a, b3) — the bilinear GLU of the transformer block — as one dual-B tcgen05 kernel
+Tensor gemm_glu(const Tensor &a, const Tensor &b1, const Tensor &b3) {
+    require_device(a, "gemm_glu");
+    KF_CHECK(a.is_contiguous() && b1.is_contiguous() && b3.is_contiguous(), "gemm: operands must be contiguous");
+    KF_CHECK(b1.dim() == 2 && a.dim() >= 2 && b1.size(0) == a.size(-1) && b3.sizes() == b1.sizes(), "gemm_glu: b1, b3 must be [K, N]");
+    KF_CHECK(a.dtype() == b1.dtype() && a.dtype() == b3.dtype(), "gemm: dtype mismatch");
+    const bool rg = any_requires_grad({&a, &b1, &b3});
+    auto oshape = a.sizes();
+    oshape.back() = b1.size(1);
+    Tensor out = empty(oshape, a.dtype(), a.device());
+    Tensor u, v;
+    if (rg) {
+        u = empty(oshape, a.dtype(), a.device());
+        v = empty(oshape, a.dtype(), a.device());
+    }
+    GemmPlan p{};
+    p.a = a.data(); p.b = b1.data(); p.b2 = b3.data(); p.c = out.data();
+    p.dtype = a.dtype();
+    p.K = a.size(-1); p.N = b1.size(1); p.M = p.K ? a.numel() / p.K : 0; p.batch = 1;
+    p.lda = p.K; p.ldb = p.N; p.ldc = p.N;
+    p.sc = p.M * p.N;
+    p.alpha = 1.f; p.beta = 0.f;
+    p.glu_u = rg ? u.data() : nullptr;
+    p.glu_v = rg ? v.data() : nullptr;
+    if (out.numel() == 0 || !launch_gemm_glu_tc(p)) {  // shapes / dtypes the dual-B kernel does not take: three launches
+        Tensor uu = matmul_nograd(a, false, b1, false, 1.f, 0.f, nullptr), vv = matmul_nograd(a, false, b3, false, 1.f, 0.f, nullptr);
+        u = uu; v = vv;
+        run_binary(EW_MUL, out, uu, vv);
+    }
+    if (rg) {
+        auto *fn = new GluGrad();
+        fn->a = a.detach(); fn->b1 = b1.detach(); fn->b3 = b3.detach();
+        fn->u = u; fn->v = v;
+        attach(out, fn, {a, b1, b3});
     }
     return out;
 }
@@ -977,6 +1191,7 @@ void backward(Tensor &root, const Tensor &grad_output) {
             for (size_t i = 0; i < inputs.size(); ++i) {
                 if (!inputs[i].requires_grad()) continue;
                 KF_CHECK(i < gis.size() && gis[i].defined(), t->grad_fn->name(), " produced no gradient for input ", i);
+                KF_CHECK(gis[i].sizes() == inputs[i].sizes(), t->grad_fn->name(), " produced a gradient of the wrong shape for input ", i);
                 Tensor &acc = grad_acc[inputs[i].impl.get()];
                 acc = acc.defined() ? binary(EW_ADD, acc.detach(), gis[i].detach()) : gis[i].detach();
                 if (--needed[inputs[i].impl.get()] == 0) ready.push(&inputs[i]);

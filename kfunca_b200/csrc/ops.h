@@ -38,6 +38,7 @@ Tensor sum_to_shape(const Tensor &grad, const std::vector<int64_t> &shape);
 
 // ---- fused layer norm over the last dim (gain has E elements); differentiable in x and gain
 Tensor layer_norm(const Tensor &x, const Tensor &gain, double eps);
+Tensor rms_norm(const Tensor &x, const Tensor &gain, double eps);
 
 // ---- sort / top-k
 std::tuple<Tensor, Tensor> sort(const Tensor &self, int64_t dim, bool descending);
@@ -47,16 +48,26 @@ std::tuple<Tensor, Tensor> topk(const Tensor &self, int64_t k, int64_t dim, bool
 Tensor cat(const std::vector<Tensor> &tensors, int64_t dim);
 std::vector<Tensor> split(const Tensor &self, const std::vector<int64_t> &sizes, int64_t dim);
 Tensor &index_put_(Tensor &self, const std::vector<Tensor> &indices, const Tensor &values);
+// out[..., :] = weight[indices[...], :]; differentiable in weight (deterministic scatter-add)
+Tensor embedding(const Tensor &weight, const Tensor &indices);
+// counter-based uniform fill, element i = lo + (hi - lo) * u(i, seed): reproducible on the host (oracle.counter_uniform), used to
+// build the BASELINE-size inputs (C4: 8.6 GB) on the device instead of uploading them
+Tensor &random_uniform_(Tensor &self, uint64_t seed, double lo, double hi);
 // differentiable view wrappers (the raw view algebra on Tensor carries no grad_fn)
 Tensor permute(const Tensor &self, const std::vector<int64_t> &dims);
 Tensor view(const Tensor &self, const std::vector<int64_t> &sizes);
 Tensor contiguous(const Tensor &self);
 Tensor slice(const Tensor &self, int64_t dim, int64_t start, int64_t end, int64_t step);
+Tensor narrow(const Tensor &self, int64_t dim, int64_t start, int64_t length);
+Tensor select(const Tensor &self, int64_t dim, int64_t index);
 
 // ---- contractions
 Tensor gemm(const Tensor &a, const Tensor &b, float alpha, float beta);
 void gemm_out(Tensor &out, const Tensor &a, const Tensor &b, float alpha, float beta);
 Tensor matmul(const Tensor &a, bool trans_a, const Tensor &b, bool trans_b, float alpha);
+// fused epilogues: alpha * a @ b + residual, and the GLU product gemm(a, b1) * gemm(a, b3); bit-identical to the composed forms
+Tensor gemm_residual(const Tensor &a, const Tensor &b, const Tensor &residual, float alpha);
+Tensor gemm_glu(const Tensor &a, const Tensor &b1, const Tensor &b3);
 // operands and result in (pinned) host memory; uploads, slab products and downloads overlap on three streams
 void gemm_host(const void *a_host, const void *b_host, void *c_host, int64_t M, int64_t N, int64_t K, DType dtype, float alpha,
                int64_t slab_rows);

@@ -304,6 +304,26 @@ PYBIND11_MODULE(_kfunca, m) {
         ck(kf_layer_norm(x.get(), gain.get(), eps, &h));
         return PyTensor(h);
     });
+    m.def("rms_norm", [](const PyTensor &x, const PyTensor &gain, double eps) {
+        kf_tensor_t h;
+        ck(kf_rms_norm(x.get(), gain.get(), eps, &h));
+        return PyTensor(h);
+    });
+    m.def("gemm_residual", [](const PyTensor &a, const PyTensor &b, const PyTensor &r, float alpha) {
+        kf_tensor_t h;
+        ck(kf_gemm_residual(a.get(), b.get(), r.get(), alpha, &h));
+        return PyTensor(h);
+    });
+    m.def("gemm_glu", [](const PyTensor &a, const PyTensor &b1, const PyTensor &b3) {
+        kf_tensor_t h;
+        ck(kf_gemm_glu(a.get(), b1.get(), b3.get(), &h));
+        return PyTensor(h);
+    });
+    m.def("embedding", [](const PyTensor &w, const PyTensor &idx) {
+        kf_tensor_t h;
+        ck(kf_embedding(w.get(), idx.get(), &h));
+        return PyTensor(h);
+    });
     m.def("rsqrt", [](const PyTensor &a) { kf_tensor_t h; ck(kf_unary(KF_UOP_RSQRT, a.get(), &h)); return PyTensor(h); });
     m.def("neg", [](const PyTensor &a) { kf_tensor_t h; ck(kf_unary(KF_UOP_NEG, a.get(), &h)); return PyTensor(h); });
     m.def("promote_types", [](kf_dtype_t a, kf_dtype_t b) { int o; ck(kf_promote_types(a, b, &o)); return (kf_dtype_t)o; });
@@ -441,6 +461,10 @@ PYBIND11_MODULE(_kfunca, m) {
             std::vector<kf_tensor_t> hs;
             for (auto &t : indices) hs.push_back(t.get());
             ck(kf_index_put_(self.get(), hs.data(), (int)hs.size(), values.get()));
+            return self;
+        })
+        .def("random_uniform_", [](PyTensor &self, uint64_t seed, double lo, double hi) {
+            ck(kf_random_uniform_(self.get(), seed, lo, hi));
             return self;
         })
         .def("half", [](const PyTensor &self) { kf_tensor_t h; ck(kf_convert(self.get(), KF_HALF, &h)); return PyTensor(h); })

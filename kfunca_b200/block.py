@@ -27,8 +27,14 @@ def _norm_fused(x, gain, eps=1e-5):
 
 
 class Block:
-    def __init__(self, E: int, H: int, dtype=None, device: int = 0, seed: int = 0, ffn_mult: int = 4, fused_norm: bool = True):
+    def __init__(self, E: int, H: int, dtype=None, device: int = 0, seed: int = 0, ffn_mult: int = 4, fused_norm: bool = True,
+                 fused: bool = True):
+        """fused=True (default) uses the fused linear ops of SURVEY §8f rank 4 — `gemm_residual` (x + gemm in the GEMM epilogue),
+        `gemm_glu` (both GLU products and their multiply in one dual-B kernel) and `qkv_attention` (attention reading q, k, v in
+        place from the packed qkv GEMM output and writing [B, S, E] directly: no head transposes in either direction);
+        fused=False is the same block written only with the reference's own operator names (register.cpp)."""
         assert E % H == 0
+        self.fused = fused
         self.norm = _norm_fused if fused_norm else _norm
         self.E, self.H, self.D, self.F = E, H, E // H, ffn_mult * E
         self.dtype = dtype or kf.bfloat16
@@ -54,10 +60,18 @@ class Block:
         H, D = self.H, self.D
         xn = self.norm(x, p["g1"])
         qkv = kf.gemm(xn, p["wqkv"], 1.0, 0.0)
-        q, k, v = qkv.split([E, E, E], -1)
-        heads = lambda t: t.contiguous().view(B, S, H, D).permute(0, 2, 1, 3).contiguous()
-        o = kf.causal_attention(heads(q), heads(k), heads(v))
-        o = o.permute(0, 2, 1, 3).contiguous().view(B, S, E)
+        if self.fused and hasattr(kf, "qkv_attention"):
+            o = kf.qkv_attention(qkv, H)  # [B, S, 3E] -> [B, S, E]
+        else:
+            q, k, v = qkv.split([E, E, E], -1)
+            heads = lambda t: t.contiguous().view(B, S, H, D).permute(0, 2, 1, 3).contiguous()
+            o = kf.causal_attention(heads(q), heads(k), heads(v))
+            o = o.permute(0, 2, 1, 3).contiguous().view(B, S, E)
+        if self.fused:
+            x1 = kf.gemm_residual(o, p["wo"], x, 1.0)
+            xn2 = self.norm(x1, p["g2"])
+            h = kf.gemm_glu(xn2, p["w1"], p["w3"])
+            return kf.gemm_residual(h, p["w2"], x1, 1.0)
         x1 = x + kf.gemm(o, p["wo"], 1.0, 0.0)
         xn2 = self.norm(x1, p["g2"])
         h = kf.gemm(xn2, p["w1"], 1.0, 0.0) * kf.gemm(xn2, p["w3"], 1.0, 0.0)

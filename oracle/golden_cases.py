@@ -44,3 +44,20 @@ def cases():
     # attention (test_nn.py:11-33), incl. the odd shape that takes the reference's fallback kernel
     for i, (b, h, sq, skv, d) in enumerate([(2, 4, 32, 256, 128), (3, 5, 64, 32, 64), (2, 3, 17, 33, 24)]):
         yield f"attn_{i}", "attention", {"q": u((b, h, sq, d), -1, 1), "k": u((b, h, skv, d), -1, 1), "v": u((b, h, skv, d))}, {}
+
+
+def cases_r2():
+    """round-2 additions: index_put_ (test_tensor.py:273-284), norm_stat (test_tensor.py:134-146) and mean_var over a
+    middle dim (test_tensor.py:120-132) -> tests/golden/ref_outputs_r2.npz"""
+    rng = np.random.default_rng(20261018)
+    u = lambda shape, lo=-10, hi=10, dt=np.float32: rng.uniform(lo, hi, size=shape).astype(dt)
+    x = u((13, 15), -10000, 10000)
+    i0, i1 = np.array([0, 5, 1, 2, 12, 7]).astype(np.int64), np.array([0, 11, 1, 0, 14, 3]).astype(np.int64)
+    yield "index_put_f32", "index_put", {"x": x, "i0": i0, "i1": i1, "values": u((6,), -10000, 10000)}, {}
+    xi = u((9, 4, 6), -100, 100, np.int32)
+    yield "index_put_i32_3d", "index_put", {"x": xi, "i0": np.array([0, 8, 3]).astype(np.int64), "i1": np.array([3, 0, 2]).astype(np.int64),
+                                          "i2": np.array([5, 5, 0]).astype(np.int64), "values": u((3,), -100, 100, np.int32)}, {}
+    yield "norm_stat_64", "norm_stat", {"x": u((64, 64))}, {}
+    yield "norm_stat_1024x2048", "norm_stat", {"x": u((1024, 2048))}, {}
+    yield "mean_var_mid", "mean_var", {"x": u((13, 325, 127))}, {"dim": 1, "take_sqrt": False}
+    yield "mean_var_last_sqrt", "mean_var", {"x": u((37, 512))}, {"dim": 1, "take_sqrt": True}

@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 
 import kfunca  # noqa: E402  (the reference)
 
-from oracle.golden_cases import cases  # noqa: E402
+from oracle.golden_cases import cases, cases_r2  # noqa: E402
 
 
 def run(kind, inp, prm):
@@ -37,14 +37,29 @@ def run(kind, inp, prm):
         return {"out": kfunca.gemm(g["a"], g["b"], 1.0, 0.0).numpy()}
     if kind == "attention":
         return {"out": kfunca.causal_attention(g["q"], g["k"], g["v"]).numpy()}
+    if kind == "index_put":
+        idx = [g[k] for k in ("i0", "i1", "i2") if k in g]
+        g["x"].index_put_(idx, g["values"])
+        return {"out": g["x"].numpy()}
+    if kind == "norm_stat":
+        # fresh pool memory: hand the pool a zeroed block first so the kernel's semaphores start at 0
+        z = kfunca.zeros([1024], kfunca.int, 0)
+        del z
+        m, i = g["x"].norm_stat(0)
+        return {"mean": m.numpy(), "invstd": i.numpy()}
+    if kind == "mean_var":
+        m, v = g["x"].mean_var(prm["dim"], prm["take_sqrt"])
+        return {"mean": m.numpy(), "var": v.numpy()}
     raise ValueError(kind)
 
 
 def main():
     out_dir = os.path.join(os.path.dirname(HERE), "gpurun_out", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    which = sys.argv[1] if len(sys.argv) > 1 else "r1"
+    gen, fname = (cases_r2, "ref_outputs_r2.npz") if which == "r2" else (cases, "ref_outputs.npz")
     blob = {}
-    for name, kind, inp, prm in cases():
+    for name, kind, inp, prm in gen():
         try:
             res = run(kind, inp, prm)
         except Exception as e:  # keep going: record what the reference cannot do
@@ -53,7 +68,7 @@ def main():
         for k, v in res.items():
             blob[f"{name}.{k}"] = v
         print("ok", name, {k: v.shape for k, v in res.items()})
-    np.savez_compressed(os.path.join(out_dir, "ref_outputs.npz"), **blob)
+    np.savez_compressed(os.path.join(out_dir, fname), **blob)
     print("wrote", len(blob), "arrays")
 
 

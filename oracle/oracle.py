@@ -227,13 +227,13 @@ def causal_attention(q: np.ndarray, k: np.ndarray, v: np.ndarray, return_lse: bo
 
     q, k, v = f64(q), f64(k), f64(v)
     sq, skv, d = q.shape[-2], k.shape[-2], q.shape[-1]
-    s = np.einsum("...md,...nd->...mn", q, k) / np.sqrt(float(d))
+    s = (q @ np.swapaxes(k, -1, -2)) / np.sqrt(float(d))  # matmul = BLAS: the S = 4096 heads of the C3 test finish in seconds
     mask = np.arange(sq)[:, None] >= np.arange(skv)[None, :]
     s = np.where(mask, s, -np.inf)
     m = s.max(axis=-1, keepdims=True)
     e = np.exp(s - m)
     l = e.sum(axis=-1, keepdims=True)
-    out = np.einsum("...mn,...nd->...md", e / l, v)
+    out = (e / l) @ v
     if return_lse:
         return out, (m + np.log(l))[..., 0]
     return out
@@ -247,17 +247,17 @@ def causal_attention_bwd(q, k, v, dout):
     q, k, v, dout = f64(q), f64(k), f64(v), f64(dout)
     sq, skv, d = q.shape[-2], k.shape[-2], q.shape[-1]
     scale = 1.0 / np.sqrt(float(d))
-    s = np.einsum("...md,...nd->...mn", q, k) * scale
+    s = (q @ np.swapaxes(k, -1, -2)) * scale
     mask = np.arange(sq)[:, None] >= np.arange(skv)[None, :]
     s = np.where(mask, s, -np.inf)
     p = np.exp(s - s.max(axis=-1, keepdims=True))
     p = p / p.sum(axis=-1, keepdims=True)
-    dv = np.einsum("...mn,...md->...nd", p, dout)
-    dp = np.einsum("...md,...nd->...mn", dout, v)
+    dv = np.swapaxes(p, -1, -2) @ dout
+    dp = dout @ np.swapaxes(v, -1, -2)
     delta = (p * dp).sum(axis=-1, keepdims=True)
     ds = p * (dp - delta) * scale
-    dq = np.einsum("...mn,...nd->...md", ds, k)
-    dk = np.einsum("...mn,...md->...nd", ds, q)
+    dq = ds @ k
+    dk = np.swapaxes(ds, -1, -2) @ q
     return dq, dk, dv
 
 
@@ -299,3 +299,77 @@ def layer_norm_bwd(x: np.ndarray, gain: np.ndarray, dy: np.ndarray, eps: float =
     dx = rstd * (gg - gg.mean(axis=-1, keepdims=True) - xh * (gg * xh).mean(axis=-1, keepdims=True))
     dgain = (dy64 * xh).reshape(-1, x64.shape[-1]).sum(axis=0)
     return dx, dgain
+
+
+def rms_norm(x: np.ndarray, gain: np.ndarray, eps: float = 1e-5) -> np.ndarray:
+    """y = x / sqrt(mean(x^2) + eps) * gain over the last dim, float64 — the op the reference's README lists as its next one
+    (README.md:28 `rms_norm`); statistics in the style of its mean_var / norm_stat kernels (reduce_ops_kernel.cu:61-153)."""
+    x64 = np.asarray(x).astype(np.float32).astype(np.float64) if np.asarray(x).dtype.itemsize == 2 else np.asarray(x).astype(np.float64)
+    g64 = np.asarray(gain).astype(np.float32).astype(np.float64).reshape(-1) if np.asarray(gain).dtype.itemsize == 2 else np.asarray(gain).astype(np.float64).reshape(-1)
+    ms = (x64 * x64).mean(axis=-1, keepdims=True)
+    return x64 / np.sqrt(ms + eps) * g64
+
+
+def rms_norm_bwd(x: np.ndarray, gain: np.ndarray, dy: np.ndarray, eps: float = 1e-5):
+    """gradients of rms_norm in float64: dx and dgain ([E])."""
+    x64, g64, dy64 = (np.asarray(t).astype(np.float64) for t in (x, gain, dy))
+    g64 = g64.reshape(-1)
+    rstd = 1.0 / np.sqrt((x64 * x64).mean(axis=-1, keepdims=True) + eps)
+    xh = x64 * rstd
+    gg = dy64 * g64
+    dx = rstd * (gg - xh * (gg * xh).mean(axis=-1, keepdims=True))
+    return dx, (dy64 * xh).reshape(-1, x64.shape[-1]).sum(axis=0)
+
+
+def norm_stat(x: np.ndarray, eps: float = 1e-12):
+    """(mean, invstd) over dim 0 of a 2-D array, keepdim, float64: biased variance, invstd = 1 / sqrt(var + eps).
+    ref: norm_stat_kernel (src/device/norm_ops_kernel.cu:6-61) + WelfordNormPFKernel (src/device/utils/welford_norm.h:25-355);
+    the reference's own test recomputes it as 1 / sqrt(sum((x - mean)^2) / R) (test/test_tensor.py:134-146)."""
+    x64 = np.asarray(x).astype(np.float64)
+    m = x64.mean(axis=0, keepdims=True)
+    v = ((x64 - m) ** 2).mean(axis=0, keepdims=True)
+    return m, 1.0 / np.sqrt(v + eps)
+
+
+def index_put(x: np.ndarray, indices, values: np.ndarray) -> np.ndarray:
+    """self[idx0[i], idx1[i], ...] = values[i] on a copy; negative indices wrap.  ref: index_put_kernel /
+    IndexElementwiseKernel (src/device/utils/tensor_index.h:19-143, src/core/index_ops.cpp:6-38).  Duplicate index tuples are
+    unspecified in the reference (last writer wins on the GPU); tests use distinct tuples."""
+    out = np.array(x, copy=True)
+    idx = tuple(np.where(np.asarray(ix) < 0, np.asarray(ix) + out.shape[d], np.asarray(ix)) for d, ix in enumerate(indices))
+    out[idx] = np.asarray(values).reshape(-1)
+    return out
+
+
+def embedding(weight: np.ndarray, idx: np.ndarray) -> np.ndarray:
+    """out[..., :] = weight[idx[...], :] (the gather direction of the reference's index kernels, tensor_index.h:19-143;
+    README.md:30 `embedding`).  Negative ids wrap."""
+    idx = np.asarray(idx)
+    return weight[np.where(idx < 0, idx + weight.shape[0], idx)]
+
+
+def embedding_bwd(idx: np.ndarray, grad: np.ndarray, V: int) -> np.ndarray:
+    """dW[v] = sum of grad rows whose id is v, accumulated in ascending position order in float32 (16-bit and fp32 inputs) or
+    float64 — the same order and precision as the deterministic device kernel, so fp32 results can be compared bit for bit."""
+    idx = np.asarray(idx).reshape(-1)
+    g = np.asarray(grad).reshape(idx.size, -1)
+    acc_t = np.float64 if g.dtype == np.float64 else np.float32
+    dw = np.zeros((V, g.shape[1]), dtype=acc_t)
+    for p in range(idx.size):  # small cases only
+        dw[idx[p] if idx[p] >= 0 else idx[p] + V] += g[p].astype(acc_t)
+    return dw.astype(g.dtype)
+
+
+def counter_uniform(start: int, count: int, seed: int, lo: float, hi: float) -> np.ndarray:
+    """Host twin of kf_random_uniform_ (kernels/misc.cu fill_random_kernel): element i = lo + (hi - lo) * u_i in float32 with a
+    separately rounded multiply and add, u_i = top 24 bits of splitmix64(i + seed * golden) * 2^-24.  Returns elements
+    [start, start + count) as float32.  Test infrastructure: lets the BASELINE-size inputs be generated on the device and any
+    sampled row be re-created on the host."""
+    with np.errstate(over="ignore"):
+        z = np.arange(start, start + count, dtype=np.uint64) + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    u = (z >> np.uint64(40)).astype(np.float32) * np.float32(5.9604644775390625e-8)
+    span = np.float32(np.float32(hi) - np.float32(lo))
+    return (np.float32(lo) + (span * u).astype(np.float32)).astype(np.float32)

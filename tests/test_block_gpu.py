@@ -43,7 +43,7 @@ def host(t):
 @pytest.mark.parametrize("dtype,B,S,E,H,tol", [("float", 2, 64, 128, 2, 2e-4), ("bfloat16", 2, 256, 256, 2, 3e-2)])
 def test_block_forward_backward_matches_torch_autograd(dtype, B, S, E, H, tol, fused):
     kdt = getattr(kf, dtype)
-    blk = Block(E, H, dtype=kdt, device=0, seed=3, fused_norm=fused)
+    blk = Block(E, H, dtype=kdt, device=0, seed=3, fused_norm=fused, fused=fused)
     rng = np.random.default_rng(5)
     x_np = rng.uniform(-1, 1, (B, S, E)).astype(np.float32)
     x = kf.from_numpy(x_np, 0).to(kdt)

@@ -168,3 +168,77 @@ def test_oracle_layer_norm_and_mean_var_vs_torch():
     np.testing.assert_allclose(v, torch.tensor(x).var(1, unbiased=True, keepdim=True).numpy(), rtol=1e-12)
     _, sd = O.mean_var(x, 2, True)
     np.testing.assert_allclose(sd, torch.tensor(x).std(2, unbiased=True, keepdim=True).numpy(), rtol=1e-12)
+
+
+def test_oracle_round2_functions_vs_torch():
+    """rms_norm (+ backward), norm_stat, index_put, embedding (+ backward) against torch-CPU float64 — the same way the reference's
+    tests pin their expectations (test/test_tensor.py:134-146, 273-284)."""
+    import torch
+
+    rng = np.random.default_rng(33)
+    x, gain, dy = rng.uniform(-3, 3, (6, 5, 64)), rng.uniform(0.5, 1.5, (64,)), rng.uniform(-1, 1, (6, 5, 64))
+    tx, tg = torch.tensor(x, requires_grad=True), torch.tensor(gain, requires_grad=True)
+    ty = tx * torch.rsqrt((tx * tx).mean(-1, keepdim=True) + 1e-5) * tg
+    ty.backward(torch.tensor(dy))
+    np.testing.assert_allclose(O.rms_norm(x, gain, 1e-5), ty.detach().numpy(), rtol=1e-12, atol=1e-12)
+    dx, dg = O.rms_norm_bwd(x, gain, dy, 1e-5)
+    np.testing.assert_allclose(dx, tx.grad.numpy(), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(dg, tg.grad.numpy(), rtol=1e-10, atol=1e-12)
+    a = rng.uniform(-10, 10, (300, 17))
+    m, inv = O.norm_stat(a)
+    np.testing.assert_allclose(m, a.mean(0, keepdims=True), rtol=1e-12)
+    np.testing.assert_allclose(inv, 1.0 / np.sqrt(((a - a.mean(0)) ** 2).sum(0, keepdims=True) / 300), rtol=1e-9)  # test_tensor.py:141-143
+    base = rng.uniform(-1e4, 1e4, (13, 15)).astype(np.float32)
+    i0, i1 = np.array([0, 5, 1, 2]), np.array([0, 11, 1, 0])
+    vals = rng.uniform(-1e4, 1e4, 4).astype(np.float32)
+    want = torch.from_numpy(base.copy())
+    want.index_put_([torch.from_numpy(i0), torch.from_numpy(i1)], torch.from_numpy(vals))
+    np.testing.assert_array_equal(O.index_put(base, [i0, i1], vals), want.numpy())
+    w = rng.uniform(-1, 1, (20, 8))
+    idx = rng.integers(0, 20, (3, 7))
+    tw = torch.tensor(w, requires_grad=True)
+    go = rng.uniform(-1, 1, (3, 7, 8))
+    te = torch.nn.functional.embedding(torch.from_numpy(idx), tw)
+    te.backward(torch.tensor(go))
+    np.testing.assert_array_equal(O.embedding(w, idx), te.detach().numpy())
+    np.testing.assert_allclose(O.embedding_bwd(idx, go, 20), tw.grad.numpy(), rtol=1e-12, atol=1e-12)
+
+
+def test_oracle_counter_uniform_properties():
+    a = O.counter_uniform(0, 100000, 5, -2.0, 3.0)
+    assert a.dtype == np.float32 and a.min() >= -2.0 and a.max() < 3.0
+    assert abs(float(a.mean()) - 0.5) < 0.02 and np.unique(a).size > 99000
+    np.testing.assert_array_equal(O.counter_uniform(1000, 50, 5, -2.0, 3.0), a[1000:1050])      # random access = sequential
+    assert not np.array_equal(O.counter_uniform(0, 100, 6, -2.0, 3.0), a[:100])                   # the seed matters
+    big = O.counter_uniform((1 << 31) + 7, 4, 5, -1.0, 1.0)                                        # indices beyond 2^31
+    assert np.all(np.isfinite(big))
+
+
+def test_oracle_against_reference_build_outputs_round2():
+    """replay of tests/golden/ref_outputs_r2.npz: outputs of the UNMODIFIED reference build (oracle/_ref) on a B200 for
+    index_put_, norm_stat and mean_var (oracle/make_golden_from_ref.py r2)."""
+    import os
+
+    from oracle.golden_cases import cases_r2
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_outputs_r2.npz")
+    if not os.path.exists(path):
+        pytest.skip("ref_outputs_r2.npz not generated yet")
+    gold = np.load(path)
+    seen = 0
+    for name, kind, inp, prm in cases_r2():
+        if kind == "index_put" and f"{name}.out" in gold:
+            idx = [inp[k] for k in ("i0", "i1", "i2") if k in inp]
+            np.testing.assert_array_equal(O.index_put(inp["x"], idx, inp["values"]), gold[f"{name}.out"])
+            seen += 1
+        elif kind == "norm_stat" and f"{name}.mean" in gold:
+            m, inv = O.norm_stat(inp["x"])
+            np.testing.assert_allclose(gold[f"{name}.mean"], m, rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(gold[f"{name}.invstd"], inv, rtol=1e-4)
+            seen += 1
+        elif kind == "mean_var" and f"{name}.mean" in gold:
+            m, v = O.mean_var(inp["x"], prm["dim"], prm["take_sqrt"])
+            np.testing.assert_allclose(gold[f"{name}.mean"], m, rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(gold[f"{name}.var"], v, rtol=1e-4)
+            seen += 1
+    assert seen >= 1

@@ -102,34 +102,42 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+DIST_BACKEND = "none (1 GPU)"
+
+
 def dist_setup(n):
+    """N > 1: the library's native NCCL layer (kfunca_b200.dist -> csrc/dist.cpp; rendezvous over std-lib TCP, no torch).  If that
+    cannot initialise on this box the round-1 torch.distributed plumbing (tools/torch_dist_fallback.py) takes over and the JSON
+    line says so."""
+    global DIST_BACKEND
     if n <= 1:
         return 0, 1, None
-    import torch
-    import torch.distributed as dist
+    if os.environ.get("KF_DIST", "native") != "torch":
+        try:
+            from kfunca_b200 import dist as kd
 
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    return rank, world, dist
+            rank, world, _ = kd.init_from_env()
+            import kfunca_b200 as kf
+
+            DIST_BACKEND = f"native NCCL {kf.dist_info()[3]} (csrc/dist.cpp)"
+            return rank, world, kd
+        except Exception as e:  # pragma: no cover - only on a box without a usable libnccl
+            print(f"[bench] native NCCL layer unavailable ({e!r}); falling back to torch.distributed", file=sys.stderr)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import torch_dist_fallback as kd
+
+    rank, world, _ = kd.init_from_env()
+    DIST_BACKEND = "torch.distributed (fallback)"
+    return rank, world, kd
 
 
 def max_over_ranks(ms, dist):
-    if dist is None:
-        return ms
-    import torch
-
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+    return ms if dist is None else dist.max_over_ranks(ms)
 
 
 def barrier(dist):
     if dist is not None:
-        import torch
-
         dist.barrier()
-        torch.cuda.synchronize()
 
 
 def best_of(fn, reps=3):
@@ -258,7 +266,7 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "bf16 matmul M=N=K=8192 per GPU (BASELINE.json configs[1]); A,B,C row-major, B is [K,N]",
                    "l2": "A+B = 256 MiB > 126 MB L2, no flush needed", "seed": 1234, "parity_spot_check": parity_ok,
-                   "parallelism": f"dp{world} (independent M-slabs, no collective)"},
+                   "parallelism": f"dp{world} (independent M-slabs, no collective)", "dist_backend": DIST_BACKEND},
         "e2e": {"value": round(e2e_val, 2), "unit": "TFLOP/s", "h2d_bytes_per_step": 2 * n * n * 2, "d2h_bytes_per_step": n * n * 2,
                 "ms_per_step": round(max(e2e_ms, e2e_wall_ms), 3), "api": "kf_gemm_host (pinned host A, B, C; upload / slab GEMM / download overlapped)",
                 "matches_device_path": e2e_same, "sequential_ms_per_step": round(seq_ms, 3)},
@@ -290,7 +298,7 @@ def time_block(kf, Event, dist, rank, world, steps, warmup, global_batch=8, S=40
     """C5 (BASELINE.json configs[4]): transformer block fwd+bwd, bf16, batch-sharded (global batch fixed = strong scaling);
     the weight-gradient all-reduce and the cross-shard loss mean go through NCCL inside the timed region."""
     from kfunca_b200.block import Block
-    from kfunca_b200.dist import all_reduce_grads, all_reduce_mean_scalar, shard_bounds
+    from kfunca_b200.dist import shard_bounds
 
     local = int(os.environ.get("LOCAL_RANK", 0))
     lo, hi = shard_bounds(global_batch, rank, world)
@@ -301,8 +309,7 @@ def time_block(kf, Event, dist, rank, world, steps, warmup, global_batch=8, S=40
 
     overlap = os.environ.get("KF_DP_OVERLAP", "1") == "1" and world > 1  # default on; KF_DP_OVERLAP=0 = all-reduce after backward
     if overlap:
-        from kfunca_b200.dist import OverlappedGradAllReduce
-        ar = OverlappedGradAllReduce(blk.params, world, dist)
+        ar = dist.OverlappedGradAllReduce(blk.params)
 
     def step():
         if overlap:  # all-reduce of each gradient starts under the rest of the backward pass
@@ -310,8 +317,9 @@ def time_block(kf, Event, dist, rank, world, steps, warmup, global_batch=8, S=40
                 loss = blk.step(x)
         else:
             loss = blk.step(x)
-            all_reduce_grads(blk.params, world, dist)
-        return all_reduce_mean_scalar(loss, world, dist)
+            if dist is not None:
+                dist.all_reduce_grads(blk.params)
+        return dist.all_reduce_mean_scalar(loss) if dist is not None else loss
 
     for _ in range(max(warmup, 3)):
         step()
@@ -344,7 +352,7 @@ def time_block(kf, Event, dist, rank, world, steps, warmup, global_batch=8, S=40
             "launches_per_step": int(launches), "host_issue_ms_per_step": round(statistics.median(host_ms), 3),
             "loss": lossv, "finite": bool(np.isfinite(lossv)),
             "allreduce_bytes_per_step": 2 * sum(int(p.numel()) for p in blk.params.values()) if world > 1 else 0,
-            "allreduce_overlap": bool(overlap)}
+            "allreduce_overlap": bool(overlap), "dist_backend": DIST_BACKEND}
 
 
 def run_block(args):

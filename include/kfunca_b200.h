@@ -213,6 +213,24 @@ int kf_zero_grad(kf_tensor_t self);
 typedef void (*kf_leaf_grad_hook_t)(kf_tensor_t leaf, kf_tensor_t grad, void *ctx);
 int kf_set_leaf_grad_hook(kf_leaf_grad_hook_t fn, void *ctx);
 
+/* ---- data-parallel layer (no reference counterpart: SURVEY 8e; the reference is single-GPU, launcher_cuda.h:105-354) -----------
+ * One process per GPU.  NCCL (dlopen'ed libnccl.so.2) over NVLink / NVSwitch on a library-owned communication stream.
+ * Rendezvous is the caller's business: rank 0 obtains a 128-byte id and ships it to the other ranks (kfunca_b200/dist.py does it
+ * over a TCP socket on MASTER_ADDR), then every rank calls kf_dist_init after kf_set_device. */
+int kf_dist_unique_id(void *out128);
+int kf_dist_init(const void *id128, int rank, int world);
+int kf_dist_finalize(void);
+int kf_dist_info(int *initialised, int *rank, int *world, int *nccl_version);
+typedef enum { KF_RED_SUM = 0, KF_RED_AVG = 1, KF_RED_MAX = 2 } kf_red_op_t;
+/* in-place all-reduce on the LIBRARY stream (ordered with the kernels around it): the cross-shard sum / mean of SURVEY 8e */
+int kf_dist_all_reduce(kf_tensor_t t, int op);
+/* overlapped gradient averaging: between begin and end, kf_backward starts ncclAllReduce(AVG) of the gradient of every listed
+ * parameter on the communication stream the moment that gradient has been enqueued; end makes the library stream wait for the
+ * communication stream and returns the number of gradients reduced.  Call kf_zero_grad on the parameters before each backward
+ * (gradients accumulated over several backward passes inside one begin/end would be averaged more than once). */
+int kf_dist_overlap_begin(const kf_tensor_t *params, int n);
+int kf_dist_overlap_end(int64_t *n_reduced);
+
 /* ---- host-logic probes (no GPU needed; used by the `-m "not gpu"` tests) ------------------- */
 /* broadcast + dtype promotion + dimension collapse of `a op b` exactly as the engine plans it.
  * Outputs: collapsed ndim, shape[ndim], byte strides for out/a/b [3][KF_MAX_DIMS], common dtype.

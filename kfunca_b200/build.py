@@ -18,7 +18,7 @@ CSRC = PKG / "csrc"
 BUILD = PKG / "_build"
 CUDA_HOME = Path(os.environ.get("CUDA_HOME", "/usr/local/cuda"))
 
-HOST_SRCS = ["runtime.cpp", "tensor.cpp", "plan.cpp", "ops.cpp", "api.cpp"]
+HOST_SRCS = ["runtime.cpp", "tensor.cpp", "plan.cpp", "ops.cpp", "api.cpp", "dist.cpp"]
 LIB_NAME = "libkfunca_b200.so"
 EXT_NAME = "_kfunca" + sysconfig.get_config_var("EXT_SUFFIX")
 
@@ -55,7 +55,7 @@ def write_ninja() -> Path:
         "  deps = gcc",
         "  description = CXX $in",
         "rule link_lib",
-        "  command = $nvcc -shared -o $out $in -cudart static -Xlinker -soname=" + LIB_NAME,
+        "  command = $nvcc -shared -o $out $in -cudart static -ldl -Xlinker -soname=" + LIB_NAME,
         "  description = LINK $out",
         "rule ext",
         f"  command = $cxx -O2 -std=c++17 -fPIC -shared -fvisibility=hidden -I{py_inc} -I{pb_inc} $in -o $out "

@@ -584,6 +584,51 @@ int kf_set_leaf_grad_hook(kf_leaf_grad_hook_t fn, void *ctx) {
     KF_API_END
 }
 
+// ---------------------------------------------------------------- data-parallel layer (dist.cpp)
+int kf_dist_unique_id(void *out128) {
+    KF_API_BEGIN
+    KF_CHECK(out128 != nullptr);
+    dist::unique_id(out128);
+    KF_API_END
+}
+int kf_dist_init(const void *id128, int rank, int world) {
+    KF_API_BEGIN
+    KF_CHECK(id128 != nullptr);
+    dist::init(id128, rank, world);
+    KF_API_END
+}
+int kf_dist_finalize(void) {
+    KF_API_BEGIN
+    dist::finalize();
+    KF_API_END
+}
+int kf_dist_info(int *initialised, int *rank, int *world, int *nccl_version) {
+    KF_API_BEGIN
+    if (initialised) *initialised = dist::initialised();
+    if (rank) *rank = dist::rank();
+    if (world) *world = dist::world();
+    if (nccl_version) *nccl_version = dist::initialised() ? dist::nccl_version() : 0;
+    KF_API_END
+}
+int kf_dist_all_reduce(kf_tensor_t t, int op) {
+    KF_API_BEGIN
+    dist::all_reduce(T(t), op);
+    KF_API_END
+}
+int kf_dist_overlap_begin(const kf_tensor_t *params, int n) {
+    KF_API_BEGIN
+    std::vector<Tensor> ps;
+    for (int i = 0; i < n; ++i) ps.push_back(T(params[i]));
+    dist::overlap_begin(ps);
+    KF_API_END
+}
+int kf_dist_overlap_end(int64_t *n_reduced) {
+    KF_API_BEGIN
+    const int64_t n = dist::overlap_end();
+    if (n_reduced) *n_reduced = n;
+    KF_API_END
+}
+
 // ---------------------------------------------------------------- host-logic probes
 int kf_debug_plan_binary(kf_tensor_t a, kf_tensor_t b, int *ndim, int64_t *shape, int64_t *strides3, int *common_dtype) {
     KF_API_BEGIN

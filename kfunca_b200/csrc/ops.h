@@ -85,4 +85,18 @@ using LeafGradHook = void (*)(const Tensor &leaf, const Tensor &grad, void *ctx)
 void set_leaf_grad_hook(LeafGradHook fn, void *ctx);
 
 }  // namespace ops
+
+// data-parallel layer (dist.cpp): NCCL on a library-owned communication stream
+namespace dist {
+void unique_id(void *out128);
+void init(const void *id128, int rank, int world);
+void finalize();
+bool initialised();
+int rank();
+int world();
+int nccl_version();
+void all_reduce(Tensor &t, int op);  // 0 sum, 1 avg, 2 max; in place, on the library stream
+void overlap_begin(const std::vector<Tensor> &params);
+int64_t overlap_end();
+}  // namespace dist
 }  // namespace kf

@@ -205,6 +205,7 @@ PYBIND11_MODULE(_kfunca, m) {
     m.def("empty_cache", []() { ck(kf_empty_cache()); });
     m.def("synchronize", []() { ck(kf_synchronize()); });
     m.def("set_device", [](int d) { ck(kf_set_device(d)); });
+    m.def("get_device", []() { int d; ck(kf_get_device(&d)); return d; });
     m.def("device_count", []() { int n; ck(kf_device_count(&n)); return n; });
     m.def("launch_count", []() { int64_t n; ck(kf_launch_count(&n)); return n; });
     // set_leaf_grad_hook(fn | None): fn(leaf, grad) is called inside backward() as each leaf gradient is enqueued (see the header)
@@ -304,6 +305,30 @@ PYBIND11_MODULE(_kfunca, m) {
         ck(kf_layer_norm(x.get(), gain.get(), eps, &h));
         return PyTensor(h);
     });
+    // data-parallel layer (csrc/dist.cpp)
+    m.def("dist_unique_id", []() {
+        char id[128];
+        ck(kf_dist_unique_id(id));
+        return py::bytes(id, 128);
+    });
+    m.def("dist_init", [](py::bytes id, int rank, int world) {
+        std::string s = id;
+        if (s.size() != 128) throw std::runtime_error("dist_init: the id must be 128 bytes");
+        ck(kf_dist_init(s.data(), rank, world));
+    });
+    m.def("dist_finalize", []() { ck(kf_dist_finalize()); });
+    m.def("dist_info", []() {
+        int i, r, w, v;
+        ck(kf_dist_info(&i, &r, &w, &v));
+        return py::make_tuple(i != 0, r, w, v);
+    });
+    m.def("dist_all_reduce", [](PyTensor &t, int op) { ck(kf_dist_all_reduce(t.get(), op)); return t; });
+    m.def("dist_overlap_begin", [](std::vector<PyTensor> params) {
+        std::vector<kf_tensor_t> hs;
+        for (auto &t : params) hs.push_back(t.get());
+        ck(kf_dist_overlap_begin(hs.data(), (int)hs.size()));
+    });
+    m.def("dist_overlap_end", []() { int64_t n; ck(kf_dist_overlap_end(&n)); return n; });
     m.def("rms_norm", [](const PyTensor &x, const PyTensor &gain, double eps) {
         kf_tensor_t h;
         ck(kf_rms_norm(x.get(), gain.get(), eps, &h));

@@ -1,39 +1,20 @@
-"""Data-parallel plumbing: one process per GPU, NCCL over NVLink through torch.distributed.
-Only two exchanges exist on this path: the weight-gradient all-reduce and the cross-shard
-full-tensor sum/mean.  Device memory stays owned by kfunca_b200's pool; torch only sees aliases of it."""
+"""Data-parallel plumbing: one process per GPU, NCCL over NVLink through the library's own native layer
+(csrc/dist.cpp, C ABI kf_dist_*).  No torch anywhere on this path: the rendezvous is a few lines of std-lib TCP (rank 0 hands the
+128-byte NCCL id to the other ranks on MASTER_ADDR), the collectives are ncclAllReduce calls issued by the library on its own
+streams, and the gradient all-reduce is started from inside backward() by a native leaf-gradient hook.
+Only two exchanges exist on this path: the weight-gradient all-reduce and the cross-shard full-tensor sum/mean."""
 from __future__ import annotations
 
-import numpy as np
+import os
+import socket
+import struct
+import time
 
 import kfunca_b200 as kf
 
-_TYPESTR = {kf.float: "<f4", kf.double: "<f8", kf.half: "<f2", kf.bfloat16: "<i2", kf.int: "<i4", kf.long: "<i8",
-            kf.short: "<i2", kf.char: "|i1", kf.byte: "|u1", kf.bool: "|b1"}
-
-
-class _CAI:
-    def __init__(self, t):
-        assert t.is_contiguous()
-        self.__cuda_array_interface__ = {"shape": tuple(t.sizes()), "typestr": _TYPESTR[t.dtype()], "data": (t.data_ptr(), False),
-                                         "version": 2, "strides": None}
-        self._keep = t
-
-
-def as_torch(t):
-    """Zero-copy torch alias of a contiguous kfunca_b200 tensor (bf16 travels as int16 and is re-viewed)."""
-    import torch
-
-    out = torch.as_tensor(_CAI(t), device=f"cuda:{t.device()}")
-    if t.dtype() == kf.bfloat16:
-        out = out.view(torch.bfloat16)
-    return out
-
-
-def library_stream():
-    """torch view of the library's compute stream, so collectives are ordered with our kernels."""
-    import torch
-
-    return torch.cuda.ExternalStream(kf.stream())
+SUM, AVG, MAX = 0, 1, 2
+_ID_BYTES = 128
+_PORT_OFFSET = 137  # the id exchange listens on MASTER_PORT + this (MASTER_PORT itself belongs to the launcher's store)
 
 
 def shard_bounds(total: int, rank: int, world: int) -> tuple[int, int]:
@@ -46,115 +27,138 @@ def shard_bounds(total: int, rank: int, world: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def global_mean_from_partials(local_sum, local_count: int, dist):
-    """Cross-shard mean = all-reduce(sum of local sums) / all-reduce(sum of local counts) — NOT the mean of
-    per-shard means, which is wrong for unequal shards.  `local_sum` is a torch tensor on any
-    device the process group's backend supports (NCCL: cuda, gloo: cpu); it is reduced in place."""
-    import torch
-
-    cnt = torch.tensor([float(local_count)], dtype=torch.float64, device=local_sum.device)
-    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(local_sum)
-        dist.all_reduce(cnt)
-    return local_sum / cnt.to(local_sum.dtype)
+def global_mean_from_partials(local_sum: float, local_count: float, all_reduce_sum) -> float:
+    """Cross-shard mean = all-reduce(sum of local sums) / all-reduce(sum of local counts) — NOT the mean of per-shard means,
+    which is wrong for unequal shards.  `all_reduce_sum(list[float]) -> list[float]` is the collective (NCCL through
+    kf.dist_all_reduce on the GPU path, anything else in the CPU tests)."""
+    s, n = all_reduce_sum([float(local_sum), float(local_count)])
+    return s / n
 
 
-def average_gradients_(grads, dist) -> None:
-    """In-place sum-all-reduce of a list of torch gradient tensors followed by 1/world (data-parallel average)."""
-    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
-        return
-    world = dist.get_world_size()
-    for g in grads:
-        dist.all_reduce(g)
-        g.mul_(1.0 / world)
-
-
-def all_reduce_grads(params, world: int, dist) -> None:
-    """average every parameter gradient over the data-parallel group: one NCCL all-reduce per parameter with the AVG
-    reduction (the 1/world scale happens inside the collective, no extra pass over the gradients), issued back to back on
-    the library stream so they queue behind the backward kernels that produced them."""
-    import torch
-
+def exchange_id(payload: bytes | None, rank: int, world: int, addr: str, port: int, timeout: float = 120.0) -> bytes:
+    """rank 0 serves `payload` (the NCCL unique id) to the other world - 1 ranks over TCP; they return what they received."""
     if world == 1:
+        return payload
+    if rank == 0:
+        assert payload is not None and len(payload) == _ID_BYTES
+        srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+        srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+        srv.bind((addr, port))
+        srv.listen(world)
+        srv.settimeout(timeout)
+        seen = set()
+        try:
+            while len(seen) < world - 1:
+                conn, _ = srv.accept()
+                with conn:
+                    conn.settimeout(timeout)
+                    (peer,) = struct.unpack("<i", _recv_exact(conn, 4))
+                    conn.sendall(payload)
+                    seen.add(peer)
+        finally:
+            srv.close()
+        return payload
+    deadline = time.time() + timeout
+    while True:
+        try:
+            with socket.create_connection((addr, port), timeout=5.0) as c:
+                c.sendall(struct.pack("<i", rank))
+                return _recv_exact(c, _ID_BYTES)
+        except OSError:
+            if time.time() > deadline:
+                raise
+            time.sleep(0.05)
+
+
+def _recv_exact(conn, n: int) -> bytes:
+    buf = b""
+    while len(buf) < n:
+        chunk = conn.recv(n - len(buf))
+        if not chunk:
+            raise ConnectionError("peer closed during the id exchange")
+        buf += chunk
+    return buf
+
+
+def init_from_env() -> tuple[int, int, int]:
+    """(rank, world, local_rank) from the launcher's environment (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT);
+    selects the GPU, exchanges the NCCL id and creates the communicator.  world == 1 needs no launcher and loads no NCCL."""
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    kf.set_device(local)
+    if world > 1 and not kf.dist_info()[0]:
+        addr = os.environ.get("MASTER_ADDR", "127.0.0.1")
+        port = int(os.environ.get("MASTER_PORT", "29500")) + _PORT_OFFSET
+        uid = exchange_id(kf.dist_unique_id() if rank == 0 else None, rank, world, addr, port)
+        kf.dist_init(uid, rank, world)
+    return rank, world, local
+
+
+def finalize() -> None:
+    kf.dist_finalize()
+
+
+def all_reduce_(t, op: int = SUM):
+    """in place on the library stream (ordered with the kernels around it); no-op at world 1"""
+    return kf.dist_all_reduce(t, op)
+
+
+def barrier() -> None:
+    """every rank has enqueued and finished everything before this point"""
+    if kf.dist_info()[0]:
+        tok = kf.zeros([1], kf.float, kf.get_device())
+        kf.dist_all_reduce(tok, SUM)
+    kf.synchronize()
+
+
+def max_over_ranks(value: float) -> float:
+    if not kf.dist_info()[0]:
+        return value
+    import numpy as np
+
+    t = kf.from_numpy(np.array([value], dtype=np.float64), kf.get_device())
+    kf.dist_all_reduce(t, MAX)
+    return float(t.numpy()[0])
+
+
+def all_reduce_grads(params) -> None:
+    """average every parameter gradient over the data-parallel group AFTER the backward pass: one ncclAllReduce(AVG) per
+    parameter, back to back on the library stream (the non-overlapped baseline of OverlappedGradAllReduce)."""
+    if not kf.dist_info()[0]:
         return
-    avg = dist.ReduceOp.AVG if dist.get_backend() == "nccl" else None
-    with torch.cuda.stream(library_stream()):
-        for p in params.values():
-            g = p.grad()
-            if not g.defined():
-                continue
-            tg = as_torch(g)
-            if avg is not None:
-                dist.all_reduce(tg, op=avg)
-            else:  # gloo has no AVG
-                dist.all_reduce(tg)
-                g *= 1.0 / world
+    for p in params.values():
+        g = p.grad()
+        if g.defined():
+            kf.dist_all_reduce(g, AVG)
 
 
-def all_reduce_mean_scalar(t, world: int, dist):
-    """cross-shard mean of per-shard means with equal shard sizes: all-reduce(AVG)"""
-    import torch
-
-    if world == 1:
+def all_reduce_mean_scalar(t):
+    """cross-shard mean of per-shard means with equal shard sizes: all-reduce(AVG) of an fp32 copy"""
+    if not kf.dist_info()[0]:
         return t
     f = t.float()
-    with torch.cuda.stream(library_stream()):
-        if dist.get_backend() == "nccl":
-            dist.all_reduce(as_torch(f), op=dist.ReduceOp.AVG)
-        else:
-            dist.all_reduce(as_torch(f))
-            f *= 1.0 / world
+    kf.dist_all_reduce(f, AVG)
     return f
 
 
 class OverlappedGradAllReduce:
-    """Start the all-reduce (AVG) of every parameter gradient the moment the backward pass has enqueued it, on a side stream, so
-    NCCL over NVLink runs under the rest of the backward pass instead of after it.
+    """Start the all-reduce (AVG) of every parameter gradient the moment the backward pass has enqueued it, on the library's
+    communication stream, so NCCL over NVLink runs under the rest of the backward pass instead of after it.
 
-        with OverlappedGradAllReduce(params, world, dist):
-            loss = block.step(x)          # backward() fires the leaf-gradient hook once per parameter
-        # on exit the library stream waits for the side stream: gradients are averaged for whoever reads them next
+        with OverlappedGradAllReduce(params):
+            loss = block.step(x)          # backward() fires the native leaf-gradient hook once per parameter
+        # on exit the library stream waits for the communication stream: gradients are averaged for whoever reads them next
 
-    Mechanics: the hook (kf.set_leaf_grad_hook) records an event on the library stream, the side stream waits for it and the
-    collective is issued there.  Gradient memory is owned by the parameter until the next zero_grad(), which is ordered after
-    the join, so the pool's single-stream free rule still holds."""
+    Everything between the hook and the collective is native (csrc/dist.cpp): event on the library stream, wait on the
+    communication stream, ncclAllReduce.  zero_grad() the parameters before each backward inside the context (block.step does)."""
 
-    def __init__(self, params, world: int, dist):
-        import torch
-
-        self.world, self.dist, self.torch = world, dist, torch
-        self.ptrs = {p.data_ptr() for p in params.values()}
-        self.active = world > 1
-        if self.active:
-            self.lib = library_stream()
-            self.side = torch.cuda.Stream()
-            self.avg = dist.ReduceOp.AVG if dist.get_backend() == "nccl" else None
+    def __init__(self, params):
+        self.params = list(params.values())
         self.count = 0
 
-    def _hook(self, leaf, grad):
-        if leaf.data_ptr() not in self.ptrs:
-            return
-        torch = self.torch
-        ev = torch.cuda.Event()
-        ev.record(self.lib)
-        self.side.wait_event(ev)
-        with torch.cuda.stream(self.side):
-            tg = as_torch(grad)
-            if self.avg is not None:
-                self.dist.all_reduce(tg, op=self.avg)
-            else:
-                self.dist.all_reduce(tg)
-                tg.mul_(1.0 / self.world)
-        self.count += 1
-
     def __enter__(self):
-        if self.active:
-            self.count = 0
-            kf.set_leaf_grad_hook(self._hook)
+        kf.dist_overlap_begin(self.params)
         return self
 
     def __exit__(self, *exc):
-        if self.active:
-            kf.set_leaf_grad_hook(None)
-            self.lib.wait_stream(self.side)
+        self.count = kf.dist_overlap_end()
         return False

@@ -190,6 +190,12 @@ int kf_gemm_residual(kf_tensor_t a, kf_tensor_t b, kf_tensor_t residual, float a
 /* out = (a @ b1) * (a @ b3), the bilinear GLU, as ONE dual-B tcgen05 kernel (fp16 / bf16; other dtypes and small shapes are composed) */
 int kf_gemm_glu(kf_tensor_t a, kf_tensor_t b1, kf_tensor_t b3, kf_tensor_t *out);
 
+/* out[B,S,H*D] = causal attention over the packed projection qkv[B,S,3*H*D] (q | k | v along the last dim, as kf_gemm(x, Wqkv) produces
+ * it): the kernels read q, k, v in place through strided TMA maps and write the merged-head layout, forward and backward — the
+ * split / view / permute / contiguous chain around kf_causal_attention disappears.  Composed from those ops when the tcgen05 path
+ * does not take the dtype / head size. */
+int kf_qkv_attention(kf_tensor_t qkv, int64_t heads, kf_tensor_t *out);
+
 /* ---- embedding (ref: README.md:30 `embedding`, gather/scatter of src/device/utils/tensor_index.h:19-143,
  * src/core/index_ops.cpp:6-38) --------------------------------------------------------------------------------------------- */
 /* out[..., :] = weight[indices[...], :] (indices int64, negative wraps); differentiable in weight: the backward is a deterministic

@@ -532,6 +532,11 @@ int kf_gemm_glu(kf_tensor_t a, kf_tensor_t b1, kf_tensor_t b3, kf_tensor_t *out)
     *out = wrap(ops::gemm_glu(T(a), T(b1), T(b3)));
     KF_API_END
 }
+int kf_qkv_attention(kf_tensor_t qkv, int64_t heads, kf_tensor_t *out) {
+    KF_API_BEGIN
+    *out = wrap(ops::qkv_attention(T(qkv), heads));
+    KF_API_END
+}
 int kf_embedding(kf_tensor_t weight, kf_tensor_t indices, kf_tensor_t *out) {
     KF_API_BEGIN
     *out = wrap(ops::embedding(T(weight), T(indices)));

@@ -100,13 +100,23 @@ bool launch_gemm_tc(const GemmPlan &p);    // fp16 / bf16 tcgen05 + TMEM + TMA p
 bool launch_gemm_f32_tc(const GemmPlan &p);  // fp32 on tcgen05 through three bf16 planes per operand (6 / 9 products); false => SIMT
 void launch_gemm(const GemmPlan &p);       // dispatcher
 
-// Causal attention (top-left aligned mask, scale 1/sqrt(D)); q [BH,Sq,D], k/v [BH,Skv,D] dense.
+// Element (b, h, s, d) of a [B, H, S, D] operand lives at base + b * sb + h * sh + s * ss + d (elements; unit stride along D).
+// Dense [B,H,S,D]: {H*S*D, S*D, D}.  A packed projection [B, S, 3, H, D] gives {S*3*H*D, D, 3*H*D} with base offsets 0 / E / 2E.
+struct AttnLayout {
+    int64_t sb, sh, ss;
+};
+inline AttnLayout dense_bhsd(int64_t H, int64_t S, int64_t D) { return {H * S * D, S * D, D}; }
+inline bool is_dense_bhsd(const AttnLayout &l, int64_t H, int64_t S, int64_t D) { return l.sb == H * S * D && l.sh == S * D && l.ss == D; }
+
+// Causal attention (top-left aligned mask, scale 1/sqrt(D)); q [B,H,Sq,D], k/v [B,H,Skv,D] in the layouts lq / lk / lv.
 struct AttnPlan {
     const void *q, *k, *v;
     void *out;
     void *lse;  // [BH, Sq] natural-log row log-sum-exp, fp32 (fp64 for fp64 inputs); may be null
     int dtype;
     int64_t BH, Sq, Skv, D;
+    int64_t H = 0;            // heads per batch entry (BH = B * H); 0 => dense layouts, H irrelevant
+    AttnLayout lq{}, lk{}, lv{}, lo{};
 };
 void launch_attention_fwd(const AttnPlan &p);     // dispatcher: tcgen05 path for 16-bit D in {64,128}, else SIMT
 bool launch_attention_fwd_tc(const AttnPlan &p);  // false when the shape / dtype is not supported
@@ -116,7 +126,10 @@ struct AttnBwdPlan {
     void *dq, *dk, *dv;
     int dtype;
     int64_t BH, Sq, Skv, D;
+    int64_t H = 0;  // 0 => dense layouts
+    AttnLayout lq{}, lk{}, lv{}, lo{}, ldo{}, ldq{}, ldk{}, ldv{};
 };
+bool launch_attention_bwd_fused(const AttnBwdPlan &p);  // one-kernel backward (5 GEMMs, ordered dQ accumulation); D = 128
 bool launch_attention_bwd_tc(const AttnBwdPlan &p);  // false => caller uses the GEMM-composed generic backward
 // P = exp(S - lse) under the causal mask, in place, fp32 / fp64 (generic backward helper)
 void launch_attn_probs(void *S, const void *lse, int dtype, int64_t BH, int64_t Sq, int64_t Skv);

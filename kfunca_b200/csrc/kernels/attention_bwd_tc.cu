@@ -432,6 +432,11 @@ static void launch_bwd_mode(const AttnBwdPlan &a, const float *lse2, const float
 bool launch_attention_bwd_tc(const AttnBwdPlan &a) {
     static const bool force_generic = std::getenv("KF_ATTN_BWD_FORCE_GENERIC") != nullptr;
     if (force_generic) return false;
+    // Strided (packed-projection) operands go to the one-kernel scheme; dense ones only with KF_ATTN_BWD_FUSED=1: measured at C3
+    // (profiles/r2_attn_bwd_fused_vs_two.log) the ordered fp32 dQ hand-over through L2 makes it 5.16 ms against 3.42 ms here.
+    static const bool want_fused = std::getenv("KF_ATTN_BWD_FUSED") != nullptr;
+    if ((a.H > 0 || want_fused) && launch_attention_bwd_fused(a)) return true;
+    if (a.H > 0) return false;  // the two-kernel scheme takes dense operands only
     if (a.dtype != KF_HALF && a.dtype != KF_BFLOAT16) return false;
     if (a.D != 64 && a.D != 128) return false;
     if (a.Sq < 1 || a.Skv < 1 || a.BH < 1 || a.BH >= 65536) return false;

@@ -38,6 +38,8 @@ struct AttnTcParams {
     float scale_log2;  // softmax scale * log2(e)
     int npairs;        // 256-row query pairs per (b, h)
     int is_bf16;
+    int H;             // heads per batch entry: (b, h) = (bh / H, bh % H) for the 4-D tensor maps and the output layout
+    AttnLayout lo;     // layout of `out`
 };
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -220,6 +222,7 @@ __device__ __forceinline__ void attn_fwd_tc_body(const CUtensorMap &tmap_q, cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bh = blockIdx.x / p.npairs;
+    const int b_idx = bh / p.H, h_idx = bh % p.H;
     const int pr = p.npairs - 1 - (blockIdx.x % p.npairs);  // heaviest (longest KV range) pairs first
     const int q0 = pr * 2 * FA_BQ;
     auto blocks_of = [&](int t) {
@@ -263,7 +266,7 @@ __device__ __forceinline__ void attn_fwd_tc_body(const CUtensorMap &tmap_q, cons
             mbar_arrive_expect_tx(q_full, ntile_q * TILE_BYTES);
             for (int t = 0; t < ntile_q; ++t)
 #pragma unroll
-                for (int a = 0; a < ATOMS; ++a) tma_load_3d(sQ + t * TILE_BYTES + a * ATOM_BYTES, &tmap_q, q_full, a * 64, q0 + t * FA_BQ, bh);
+                for (int a = 0; a < ATOMS; ++a) tma_load_4d(sQ + t * TILE_BYTES + a * ATOM_BYTES, &tmap_q, q_full, a * 64, q0 + t * FA_BQ, h_idx, b_idx);
             int s = 0;
             uint32_t ph = 0;
             for (int i = 0; i < 2 * nmax; ++i) {  // K_0, V_0, K_1, V_1, ...
@@ -272,7 +275,7 @@ __device__ __forceinline__ void attn_fwd_tc_body(const CUtensorMap &tmap_q, cons
                 mbar_wait(&kv_empty[s], ph ^ 1);
                 mbar_arrive_expect_tx(&kv_full[s], TILE_BYTES);
 #pragma unroll
-                for (int a = 0; a < ATOMS; ++a) tma_load_3d(sKV + s * TILE_BYTES + a * ATOM_BYTES, tm, &kv_full[s], a * 64, kv0, bh);
+                for (int a = 0; a < ATOMS; ++a) tma_load_4d(sKV + s * TILE_BYTES + a * ATOM_BYTES, tm, &kv_full[s], a * 64, kv0, h_idx, b_idx);
                 if (++s == NS) {
                     s = 0;
                     ph ^= 1;
@@ -400,7 +403,7 @@ __device__ __forceinline__ void attn_fwd_tc_body(const CUtensorMap &tmap_q, cons
             tc_fence_after();
             const float inv_l = 1.f / l_run;
             const bool row_ok = m_row < p.Sq;
-            uint16_t *orow = reinterpret_cast<uint16_t *>(p.out) + ((int64_t)bh * p.Sq + (row_ok ? m_row : 0)) * D + h * HD;
+            uint16_t *orow = reinterpret_cast<uint16_t *>(p.out) + (int64_t)b_idx * p.lo.sb + (int64_t)h_idx * p.lo.sh + (row_ok ? m_row : 0) * p.lo.ss + h * HD;
 #pragma unroll 1
             for (int c = 0; c < HD / 32; ++c) {
                 uint32_t orr[32];
@@ -446,10 +449,18 @@ template <int D, int POLY, int NH>
 static void launch_fwd_tc(const AttnPlan &a) {
     Runtime &rt = Runtime::get();
     const bool bf16 = a.dtype == KF_BFLOAT16;
-    const CUtensorMap tq = make_tmap_3d_16bit(a.q, bf16, D, (uint64_t)a.Sq, (uint64_t)a.BH, D, (uint64_t)a.Sq * D, 64, 128);
-    const CUtensorMap tk = make_tmap_3d_16bit(a.k, bf16, D, (uint64_t)a.Skv, (uint64_t)a.BH, D, (uint64_t)a.Skv * D, 64, 128);
-    const CUtensorMap tv = make_tmap_3d_16bit(a.v, bf16, D, (uint64_t)a.Skv, (uint64_t)a.BH, D, (uint64_t)a.Skv * D, 64, 128);
+    // dense [BH, S, D] operands are the H = BH, B = 1 case of the strided 4-D maps
+    const bool dense = a.H <= 0;
+    const int64_t H = dense ? a.BH : a.H, B = a.BH / H;
+    const AttnLayout lq = dense ? AttnLayout{a.BH * a.Sq * D, a.Sq * D, D} : a.lq, lkv_d = AttnLayout{a.BH * a.Skv * D, a.Skv * D, D};
+    const AttnLayout lk = dense ? lkv_d : a.lk, lv = dense ? lkv_d : a.lv, lo = dense ? lq : a.lo;
+    auto map = [&](const void *ptr, int64_t S, const AttnLayout &l) {
+        return make_tmap_4d_16bit(ptr, bf16, D, (uint64_t)S, (uint64_t)H, (uint64_t)B, (uint64_t)l.ss, (uint64_t)l.sh, (uint64_t)l.sb, 64, 128);
+    };
+    const CUtensorMap tq = map(a.q, a.Sq, lq), tk = map(a.k, a.Skv, lk), tv = map(a.v, a.Skv, lv);
     AttnTcParams p{};
+    p.H = (int)H;
+    p.lo = lo;
     p.BH = a.BH; p.Sq = a.Sq; p.Skv = a.Skv;
     p.out = a.out;
     p.lse = reinterpret_cast<float *>(a.lse);
@@ -479,6 +490,10 @@ bool launch_attention_fwd_tc(const AttnPlan &a) {
     if (a.Sq < 1 || a.Skv < 1 || a.BH < 1 || a.BH >= 65536) return false;
     auto al = [](const void *p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
     if (!al(a.q) || !al(a.k) || !al(a.v) || !al(a.out)) return false;
+    if (a.H > 0) {  // strided operands: every stride a multiple of 8 elements (16 bytes), rows at least D apart
+        auto lok = [&](const AttnLayout &l) { return l.sb % 8 == 0 && l.sh % 8 == 0 && l.ss % 8 == 0 && l.ss >= a.D; };
+        if (a.BH % a.H != 0 || !lok(a.lq) || !lok(a.lk) || !lok(a.lv) || !lok(a.lo)) return false;
+    }
     // share of the exponentials computed on the FMA pipe instead of the MUFU unit, in eighths (KF_ATTN_POLY; measured at C3:
     // 0 -> 1066, 2 -> 1082, 3 -> 1064 TFLOP/s with the split P hand-off; default 2)
     static const int poly = std::getenv("KF_ATTN_POLY") ? std::atoi(std::getenv("KF_ATTN_POLY")) : 2;

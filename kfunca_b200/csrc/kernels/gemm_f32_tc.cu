@@ -11,11 +11,13 @@
 //
 // Two launches:
 //   split_f32_kernel   : fp32 operand -> three bf16 planes [3][batch][rows][ld8]   (HBM-bound: 4 B read + 6 B written per element)
-//   gemm_f32x_kernel   : CTA pair (cta_group::2), 256 x 256 output tile, persistent, 192 threads per CTA
-//       warp 0   TMA producer: per 64-wide k block ONE "super stage" = this CTA's A planes (3 x 128 x 64) + B planes (3 x 128 x 64),
-//                96 KB, two stages deep; bytes of both CTAs are credited to the leader's `full[s]`
-//       warp 1   MMA issuer (leader CTA): per stage 4 k-slices x NPROD plane pairs of tcgen05.mma M256 N256 K16 into TMEM
-//       warps 2-5 epilogue: tcgen05.ld -> alpha / beta -> fp32 16-byte stores, overlapped with the next tile (2 x 256 TMEM columns)
+//   gemm_f32x_kernel   : CTA pair (cta_group::2), 256 x 128 output tile, persistent, 192 threads per CTA
+//       warp 0   TMA producer: per 64-wide k block ONE "super stage" = this CTA's A planes (3 x 128 x 64) + B planes (3 x 64 x 64),
+//                72 KB, three stages deep; bytes of both CTAs are credited to the leader's `full[s]`
+//       warp 1   MMA issuer (leader CTA): per stage 4 k-slices x NPROD plane pairs of tcgen05.mma M256 N128 K16 into TMEM:
+//                a0 b0 into the "main" accumulator, every other pair into the "small" one (see F_KCHUNK below)
+//       warps 2-5 epilogue: tcgen05.ld main + small -> IEEE add -> (+ running partial of earlier K chunks) -> alpha / beta -> fp32
+//                16-byte stores, overlapped with the next chunk's MMAs (2 x 256 TMEM columns)
 //   Each operand tile is fetched once per k block and used by up to three products, so L2 -> SMEM traffic per FLOP is half of
 //   what a "K' = 6 K" formulation on the plain bf16 kernel would move.
 // Non-finite inputs: inf * b becomes inf * b0 + inf * b1 + ... = NaN when b1 and b0 differ in sign (documented deviation; the
@@ -32,14 +34,24 @@ using namespace tc;
 namespace {
 
 constexpr int F_BM = 128;   // rows of A per CTA (the pair covers 256)
-constexpr int F_BN = 256;   // output tile width; each CTA stages F_BN / 2 columns of B
+constexpr int F_BN = 128;   // output tile width; each CTA stages F_BN / 2 columns of B
 constexpr int F_BK = 64;    // one 128-byte swizzle atom of bf16
 constexpr int F_THREADS = 192;
-constexpr int F_NSTAGES = 2;
+constexpr int F_NSTAGES = 3;
 constexpr int F_PLANE_A = F_BM * F_BK * 2;         // 16 KB
-constexpr int F_PLANE_B = (F_BN / 2) * F_BK * 2;   // 16 KB
-constexpr int F_STAGE_BYTES = 3 * (F_PLANE_A + F_PLANE_B);  // 96 KB
+constexpr int F_PLANE_B = (F_BN / 2) * F_BK * 2;   // 8 KB
+constexpr int F_STAGE_BYTES = 3 * (F_PLANE_A + F_PLANE_B);  // 72 KB
 constexpr int F_SMEM_TOTAL = F_NSTAGES * F_STAGE_BYTES + 256 + 1024;
+// The tensor core adds every MMA's result to the fp32 accumulator with TRUNCATION (measured on B200, profiles/r2_f32_gemm_accuracy.md:
+// all-positive operands, K = 8192, one accumulator: 4.9e-5 relative = ~ half an ulp lost per MMA).  Two measures keep the result
+// inside the 1e-5 band whatever K is:
+//   * the leading product a0 b0 has its own accumulator; the five (eight) small products share a second one, 2^-8 smaller, so
+//     their 5x more frequent truncations cost nothing measurable;
+//   * K is cut into chunks of F_KCHUNK: each chunk's two accumulators are summed by the epilogue warps in IEEE fp32 and added to
+//     the running partial kept in C itself (read-modify-write by the same thread, L2-resident), so no accumulator ever sees
+//     more than F_KCHUNK / 16 = 128 truncating additions (<= 2.8e-6 relative even when every term has the same sign).
+constexpr int F_KCHUNK = 2048;
+constexpr int F_ACC_COLS = 2 * F_BN;  // main | small
 
 struct GemmF32Params {
     int64_t M, N, K, batch;
@@ -48,6 +60,7 @@ struct GemmF32Params {
     float alpha, beta;
     int m_tiles, n_tiles;
     int64_t total_tiles;
+    int nchunks;            // K chunks per tile
     const float *residual;  // out = alpha * acc + beta * C + residual
     int64_t ldr, sr;
     int a_nb, b_nb;      // batch entries in the plane buffers (1 when the operand is broadcast over the batch)
@@ -136,28 +149,61 @@ __device__ __forceinline__ void f32_tile_coords(int64_t t, const GemmF32Params &
     mb = band * BAND + (int)(r % band_rows);
 }
 
-// one epilogue thread = one accumulator row: TMEM -> registers (32 fp32 columns at a time) -> alpha / beta -> 16-byte stores
+// one epilogue thread = one accumulator row: TMEM (main + small, 32 fp32 columns at a time) -> IEEE add -> running partial in C
+// (chunks before the last) or alpha / beta / residual -> final store (last chunk)
 __device__ __forceinline__ void f32_epilogue_tile(const GemmF32Params &p, uint32_t taddr, int64_t row, int64_t n0, float *crow, const float *rrow,
-                                                  bool vec_ok) {
+                                                  bool vec_ok, int chunk) {
+    const bool first = chunk == 0, last = chunk == p.nchunks - 1;
+    const float beta_over_alpha = (p.beta != 0.f && p.nchunks > 1) ? p.beta / p.alpha : 0.f;
 #pragma unroll 1
     for (int c = 0; c < F_BN; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)c, r);
+        uint32_t rm[32], rs[32];
+        tmem_ld32(taddr + (uint32_t)c, rm);
+        tmem_ld32(taddr + (uint32_t)(F_BN + c), rs);
         tmem_ld_wait();
         if (row < p.M && n0 + c < p.N) {
             float v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rm[i]) + __uint_as_float(rs[i]);
             const bool full_chunk = n0 + c + 32 <= p.N;
-            if (p.beta != 0.f) {
+            const bool need_c = !first || p.beta != 0.f;
+            if (need_c) {
+                float old[32];
+                if (full_chunk && vec_ok) {
+                    const float4 *src = reinterpret_cast<const float4 *>(crow + n0 + c);
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (n0 + c + i < p.N) v[i] = fmaf(p.beta, crow[n0 + c + i], v[i]);
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 f = src[i];
+                        old[4 * i] = f.x; old[4 * i + 1] = f.y; old[4 * i + 2] = f.z; old[4 * i + 3] = f.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) old[i] = (n0 + c + i < p.N) ? crow[n0 + c + i] : 0.f;
+                }
+                if (p.nchunks == 1) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fmaf(p.beta, old[i], v[i] * p.alpha);
+                } else if (first) {  // fold beta * C_old into the running (unscaled) partial: alpha * (acc + beta / alpha * C_old)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fmaf(beta_over_alpha, old[i], v[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] += old[i];
+                }
+            } else if (p.nchunks == 1) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
             }
-            if (rrow != nullptr) {
+            if (last) {
+                if (p.nchunks > 1) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (n0 + c + i < p.N) v[i] += __ldg(rrow + n0 + c + i);
+                    for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+                }
+                if (rrow != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (n0 + c + i < p.N) v[i] += __ldg(rrow + n0 + c + i);
+                }
             }
             if (full_chunk && vec_ok) {
                 float4 *dst = reinterpret_cast<float4 *>(crow + n0 + c);
@@ -182,6 +228,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1)
 gemm_f32x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmF32Params p) {
     constexpr int NST = F_NSTAGES;
     constexpr int HALF_N = F_BN / 2;
+    constexpr int KCB = F_KCHUNK / F_BK;  // k blocks per chunk
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + NST * F_STAGE_BYTES);
@@ -208,7 +255,7 @@ gemm_f32x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc_2sm(tmem_slot, 2 * F_BN);
+    if (warp == 1) tmem_alloc_2sm(tmem_slot, 2 * F_ACC_COLS);
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
@@ -242,7 +289,7 @@ gemm_f32x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             for (int i = 0; i < F_BM / 64; ++i) tma_load_3d_2sm(sa + i * (64 * F_BK * 2), &tmap_a, fb, m0 + i * 64, k0, ca);
                         }
                         if constexpr (!B_MN) {
-                            tma_load_3d_2sm(sb, &tmap_b, fb, k0, n0, cb);  // box 64(k) x 128(n)
+                            tma_load_3d_2sm(sb, &tmap_b, fb, k0, n0, cb);  // box 64(k) x 64(n)
                         } else {
 #pragma unroll
                             for (int i = 0; i < HALF_N / 64; ++i) tma_load_3d_2sm(sb + i * (64 * F_BK * 2), &tmap_b, fb, n0 + i * 64, k0, cb);
@@ -266,10 +313,13 @@ gemm_f32x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             int acc = 0;
             uint32_t acc_ph = 0;
             for (int64_t t = cluster_id; t < p.total_tiles; t += n_clusters) {
-                mbar_wait_cluster(&tmem_empty[acc], acc_ph ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * F_BN);
                 for (int kb = 0; kb < nkb; ++kb) {
+                    const int kin = kb % KCB;  // position inside the K chunk: every chunk starts a fresh pair of accumulators
+                    if (kin == 0) {
+                        mbar_wait_cluster(&tmem_empty[acc], acc_ph ^ 1);
+                        tc_fence_after();
+                    }
+                    const uint32_t d_main = tmem_base + (uint32_t)(acc * F_ACC_COLS), d_small = d_main + (uint32_t)F_BN;
                     mbar_wait_cluster(&full[s], ph);
                     tc_fence_after();
                     const uint32_t sa0 = smem_u32(smem + s * F_STAGE_BYTES);
@@ -281,19 +331,24 @@ gemm_f32x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             const uint32_t sa = sa0 + (uint32_t)(pair_a(q) * F_PLANE_A), sb = sb0 + (uint32_t)(pair_b(q) * F_PLANE_B);
                             const uint64_t adesc = A_MN ? make_sw128_desc(sa + k * 2048, 64 * F_BK * 2, 1024) : make_sw128_desc(sa + k * 32, 0, 1024);
                             const uint64_t bdesc = B_MN ? make_sw128_desc(sb + k * 2048, 64 * F_BK * 2, 1024) : make_sw128_desc(sb + k * 32, 0, 1024);
-                            umma_f16_2sm_p(d_tmem, adesc, bdesc, idesc, (kb | k | (q - (9 - NPROD))) ? 1u : 0u, leader);
+                            if (q == 8)  // a0 b0: the leading product, alone in its accumulator
+                                umma_f16_2sm_p(d_main, adesc, bdesc, idesc, (kin | k) ? 1u : 0u, leader);
+                            else
+                                umma_f16_2sm_p(d_small, adesc, bdesc, idesc, (kin | k | (q - (9 - NPROD))) ? 1u : 0u, leader);
                         }
                     }
                     umma_commit_2sm_mc_p(&empty[s], leader);
-                    if (kb == nkb - 1) umma_commit_2sm_mc_p(&tmem_full[acc], leader);
+                    if (kin == KCB - 1 || kb == nkb - 1) {
+                        umma_commit_2sm_mc_p(&tmem_full[acc], leader);
+                        if (++acc == 2) {
+                            acc = 0;
+                            acc_ph ^= 1;
+                        }
+                    }
                     if (++s == NST) {
                         s = 0;
                         ph ^= 1;
                     }
-                }
-                if (++acc == 2) {
-                    acc = 0;
-                    acc_ph ^= 1;
                 }
             }
         }
@@ -310,18 +365,20 @@ gemm_f32x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             f32_tile_coords<8>(t, p, b, mb, nb);
             const int64_t row = (int64_t)mb * (2 * F_BM) + (int64_t)rank * F_BM + q * 32 + lane;
             const int64_t n0 = (int64_t)nb * F_BN;
-            mbar_wait_cluster(&tmem_full[acc], acc_ph);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * F_BN);
             float *crow = p.c + (int64_t)b * p.sc + row * p.ldc;
             const float *rrow = p.residual ? p.residual + (int64_t)b * p.sr + row * p.ldr : nullptr;
-            f32_epilogue_tile(p, taddr, row, n0, crow, rrow, vec_ok);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(tmem_empty0 + (uint32_t)acc * 8u);
-            if (++acc == 2) {
-                acc = 0;
-                acc_ph ^= 1;
+            for (int chunk = 0; chunk < p.nchunks; ++chunk) {
+                mbar_wait_cluster(&tmem_full[acc], acc_ph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * F_ACC_COLS);
+                f32_epilogue_tile(p, taddr, row, n0, crow, rrow, vec_ok, chunk);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tmem_empty0 + (uint32_t)acc * 8u);
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_ph ^= 1;
+                }
             }
         }
     }
@@ -329,7 +386,7 @@ gemm_f32x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     cluster_sync_all();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc_2sm(tmem_base, 2 * F_BN);
+        tmem_dealloc_2sm(tmem_base, 2 * F_ACC_COLS);
     }
 }
 
@@ -357,6 +414,7 @@ static void launch_f32x_cfg(const GemmPlan &g) {
     p.m_tiles = (int)((g.M + 2 * F_BM - 1) / (2 * F_BM));
     p.n_tiles = (int)((g.N + F_BN - 1) / F_BN);
     p.total_tiles = (int64_t)p.m_tiles * p.n_tiles * g.batch;
+    p.nchunks = (int)((g.K + F_KCHUNK - 1) / F_KCHUNK);
     p.a_nb = (int)a_nb; p.b_nb = (int)b_nb;
     p.a_bmul = (a_nb > 1 || g.batch == 1) ? 1 : 0;
     p.b_bmul = (b_nb > 1 || g.batch == 1) ? 1 : 0;
@@ -381,6 +439,7 @@ bool launch_gemm_f32_tc(const GemmPlan &g) {
     if (g.M <= 0 || g.N <= 0 || g.K <= 0) return false;
     if (g.M >= (1ll << 31) || g.N >= (1ll << 31) || g.K >= (1ll << 31) || 3 * g.batch >= 65536) return false;
     // below ~ one 128 x 128 x 256 block of work the two extra launches and the 256 x 256 tile granularity lose to the FFMA kernel
+    if (g.beta != 0.f && g.alpha == 0.f && g.K > F_KCHUNK) return false;  // beta / alpha is folded into the first K chunk
     const bool forced = mode && (std::strcmp(mode, "x6") == 0 || std::strcmp(mode, "x9") == 0);
     if (!forced && (g.M < 64 || g.N < 64 || g.K < 32 || (double)g.M * (double)g.N * (double)g.K * (double)g.batch < 128.0 * 128.0 * 256.0)) return false;
     const bool nine = mode && std::strcmp(mode, "x9") == 0;

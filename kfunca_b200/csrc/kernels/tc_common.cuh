@@ -72,6 +72,12 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap *m, const void *smem_src, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
@@ -307,6 +313,24 @@ inline CUtensorMap make_tmap_3d_16bit(const void *base, bool is_bf16, uint64_t d
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     KF_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code ", (int)r, " (dims ", d0, "x", d1, "x", d2, ", strides ",
              strides[0], ",", strides[1], ", box ", b0, "x", b1, ")");
+    return m;
+}
+
+// 4-D tiled map over a 16-bit [B, H, S, D] tensor with arbitrary (16-byte aligned) batch / head / row strides in ELEMENTS and unit
+// stride along D: dims (D, S, H, B), box (b0, b1, 1, 1), 128B swizzle.  Lets attention read q / k / v in place from a packed
+// [B, S, 3, H, D] projection (and write gradients back into one) with no head transposes.
+inline CUtensorMap make_tmap_4d_16bit(const void *base, bool is_bf16, uint64_t D, uint64_t S, uint64_t H, uint64_t B, uint64_t stride_s,
+                                      uint64_t stride_h, uint64_t stride_b, uint32_t b0, uint32_t b1) {
+    CUtensorMap m;
+    cuuint64_t dims[4] = {D, S, H, B};
+    cuuint64_t strides[3] = {stride_s * 2, stride_h * 2, stride_b * 2};
+    cuuint32_t box[4] = {b0, b1, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = get_encode_tiled()(&m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                                    const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    KF_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (4-D) failed with code ", (int)r, " (dims ", D, "x", S, "x", H, "x", B, ", strides ",
+             strides[0], ",", strides[1], ",", strides[2], ", box ", b0, "x", b1, ")");
     return m;
 }
 

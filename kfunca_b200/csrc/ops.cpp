@@ -1098,6 +1098,72 @@ Tensor causal_attention(const Tensor &q, const Tensor &k, const Tensor &v) {
     return out;
 }
 
+// ---- fused qkv attention (README.md:32 lists `qkv_linear` as the reference's next fused op): attention reads q, k, v
+// IN PLACE from the packed projection qkv [B, S, 3, H, D] (4-D TMA tensor maps with the packed strides) and writes [B, S, H * D]
+// directly; the backward writes dq, dk, dv straight into one [B, S, 3, H, D] gradient.  No split / view / permute / contiguous
+// launches in either direction (the composed form costs 3 + 1 transposes forward and 4 transposes + 3 zero-fills + 2 adds backward).
+struct QkvAttentionGrad : GradFunction {
+    Tensor qkv, out, lse;
+    int64_t H;
+    const char *name() const override { return "QkvAttentionGrad"; }
+    std::vector<Tensor> backward(const Tensor &g0) override {
+        Tensor g = g0.is_contiguous() ? g0 : clone(g0.detach());
+        const int64_t B = qkv.size(0), S = qkv.size(1), E = qkv.size(2) / 3, D = E / H;
+        Tensor dqkv = empty(qkv.sizes(), qkv.dtype(), qkv.device());
+        AttnBwdPlan p{};
+        const size_t es = qkv.itemsize();
+        const char *base = reinterpret_cast<const char *>(qkv.data());
+        char *dbase = reinterpret_cast<char *>(dqkv.data());
+        p.q = base; p.k = base + E * es; p.v = base + 2 * E * es;
+        p.out = out.data(); p.dout = g.data(); p.lse = lse.data();
+        p.dq = dbase; p.dk = dbase + E * es; p.dv = dbase + 2 * E * es;
+        p.dtype = qkv.dtype();
+        p.BH = B * H; p.Sq = S; p.Skv = S; p.D = D; p.H = H;
+        const AttnLayout packed{S * 3 * E, D, 3 * E}, merged{S * E, D, E};
+        p.lq = p.lk = p.lv = p.ldq = p.ldk = p.ldv = packed;
+        p.lo = p.ldo = merged;
+        KF_CHECK(launch_attention_bwd_tc(p), "qkv_attention backward: the fused kernel rejected a shape its forward accepted");
+        return {dqkv};
+    }
+};
+
+Tensor qkv_attention(const Tensor &qkv_, int64_t H) {
+    require_device(qkv_, "qkv_attention");
+    KF_CHECK(qkv_.dim() == 3 && H > 0 && qkv_.size(2) % (3 * H) == 0, "qkv_attention expects [B, S, 3 * H * D]");
+    const int64_t B = qkv_.size(0), S = qkv_.size(1), E = qkv_.size(2) / 3, D = E / H;
+    const bool fast = (qkv_.dtype() == KF_HALF || qkv_.dtype() == KF_BFLOAT16) && D == 128 && B * H < 65536 && B > 0 && S > 0;
+    if (fast) {
+        Tensor qkv = qkv_.is_contiguous() ? qkv_ : contiguous(qkv_);
+        Tensor out = empty({B, S, E}, qkv.dtype(), qkv.device());
+        Tensor lse = empty({B, H, S}, KF_FLOAT, qkv.device());
+        AttnPlan p{};
+        const size_t es = qkv.itemsize();
+        const char *base = reinterpret_cast<const char *>(qkv.data());
+        p.q = base; p.k = base + E * es; p.v = base + 2 * E * es;
+        p.out = out.data(); p.lse = lse.data();
+        p.dtype = qkv.dtype();
+        p.BH = B * H; p.Sq = S; p.Skv = S; p.D = D; p.H = H;
+        p.lq = p.lk = p.lv = AttnLayout{S * 3 * E, D, 3 * E};
+        p.lo = AttnLayout{S * E, D, E};
+        if (launch_attention_fwd_tc(p)) {
+            if (qkv.requires_grad()) {
+                auto *fn = new QkvAttentionGrad();
+                fn->qkv = qkv.detach();
+                fn->out = out.detach();
+                fn->lse = lse;
+                fn->H = H;
+                attach(out, fn, {qkv});
+            }
+            return out;
+        }
+    }
+    // composed form from the reference's own operator names (any dtype / head size); carries its own autograd chain
+    auto parts = split(qkv_, {E, E, E}, -1);
+    auto heads = [&](const Tensor &t) { return contiguous(permute(view(contiguous(t), {B, S, H, D}), {0, 2, 1, 3})); };
+    Tensor o = causal_attention(heads(parts[0]), heads(parts[1]), heads(parts[2]));
+    return view(contiguous(permute(o, {0, 2, 1, 3})), {B, S, E});
+}
+
 // Generic backward: the five GEMMs of attention backward issued through our own GEMM kernels on fp32 (fp64)
 // temporaries, one batch entry at a time so the S_q x S_kv scratch stays bounded.  Any shape / dtype.
 // (The reference has no attention backward at all)

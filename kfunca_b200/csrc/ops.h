@@ -72,6 +72,8 @@ Tensor gemm_glu(const Tensor &a, const Tensor &b1, const Tensor &b3);
 void gemm_host(const void *a_host, const void *b_host, void *c_host, int64_t M, int64_t N, int64_t K, DType dtype, float alpha,
                int64_t slab_rows);
 Tensor causal_attention(const Tensor &q, const Tensor &k, const Tensor &v);
+// attention over a packed projection: qkv [B, S, 3 * H * D] -> [B, S, H * D], no head transposes in either direction
+Tensor qkv_attention(const Tensor &qkv, int64_t H);
 std::tuple<Tensor, Tensor> causal_attention_fwd(const Tensor &q, const Tensor &k, const Tensor &v);
 std::tuple<Tensor, Tensor, Tensor> causal_attention_bwd(const Tensor &dout, const Tensor &q, const Tensor &k, const Tensor &v,
                                                         const Tensor &out, const Tensor &lse);

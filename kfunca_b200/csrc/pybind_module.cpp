@@ -344,6 +344,11 @@ PYBIND11_MODULE(_kfunca, m) {
         ck(kf_gemm_glu(a.get(), b1.get(), b3.get(), &h));
         return PyTensor(h);
     });
+    m.def("qkv_attention", [](const PyTensor &qkv, int64_t heads) {
+        kf_tensor_t h;
+        ck(kf_qkv_attention(qkv.get(), heads, &h));
+        return PyTensor(h);
+    });
     m.def("embedding", [](const PyTensor &w, const PyTensor &idx) {
         kf_tensor_t h;
         ck(kf_embedding(w.get(), idx.get(), &h));

@@ -142,10 +142,19 @@ def test_norm_stat(shape):  # ref: test_tensor.py:134-146
 
 
 def test_convert():  # ref: test_tensor.py:148-160
-    t = kfunca.from_numpy(U(-10, 10, (2, 3)), 0)
+    # The reference draws six unseeded values and asks (x_f64)^2 ~ half(x)^2 within 1e-3 + 1e-3 |.|, which correctly rounded fp16
+    # arithmetic itself misses for ~1 in 3 draws (|x| near 4: 2^-11 input rounding, doubled by the square, plus the output rounding).
+    # Keep its assertion, on a draw that exact IEEE half arithmetic satisfies, and pin our result to that arithmetic bit for bit.
+    while True:
+        x = U(-10, 10, (2, 3))
+        exact_half = (x.astype(np.float16) * x.astype(np.float16)).astype(np.float32)
+        if np.allclose(x * x, exact_half, rtol=1e-3, atol=1e-3):
+            break
+    t = kfunca.from_numpy(x, 0)
     h = t.half()
     t *= t
     h *= h
+    assert np.array_equal(h.float().numpy(), exact_half)
     assert_allclose(t, h.float())
     t = kfunca.from_numpy(U(-10, 10, (2, 3)), 0)
     b = t.bfloat16()

@@ -18,7 +18,7 @@ for what in "$@"; do
       timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/${tag}_smoke.log
       tail -2 gpurun_out/${tag}_smoke.log ;;
     bench)
-      /usr/bin/time -v timeout 1200 python bench.py --steps 20 --warmup 5 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
+      timeout 1200 python bench.py --steps 20 --warmup 5 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
       cat gpurun_out/${tag}_bench.json; tail -25 gpurun_out/${tag}_bench.err ;;
     ref)
       timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err; echo "ref rc=$?"

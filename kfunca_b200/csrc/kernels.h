@@ -93,6 +93,9 @@ struct GemmPlan {
     // GLU: b2 = second B operand (same layout / ldb as b); C = (A b) o (A b2); glu_u / glu_v (C's layout) receive the two factors
     const void *b2 = nullptr;
     void *glu_u = nullptr, *glu_v = nullptr;
+    // rows of the WHOLE product when this plan is one row slab of it (gemm_host): kernel selection looks at the whole problem so
+    // that every slab runs the kernel the one-piece product would (bit-identical results); 0 = this plan is the whole problem
+    int64_t route_M = 0;
 };
 bool launch_gemm_glu_tc(const GemmPlan &p);  // false => compose from two GEMMs and a multiply
 void launch_gemm_simt(const GemmPlan &p);  // fp32 / fp64 FFMA/DFMA path (strict-parity path)
@@ -130,6 +133,7 @@ struct AttnBwdPlan {
     AttnLayout lq{}, lk{}, lv{}, lo{}, ldo{}, ldq{}, ldk{}, ldv{};
 };
 bool launch_attention_bwd_fused(const AttnBwdPlan &p);  // one-kernel backward (5 GEMMs, ordered dQ accumulation); D = 128
+bool launch_attention_bwd_wide(const AttnBwdPlan &p);   // two kernels, 128 x 128 tiles, dense or strided operands (the default)
 bool launch_attention_bwd_tc(const AttnBwdPlan &p);  // false => caller uses the GEMM-composed generic backward
 // P = exp(S - lse) under the causal mask, in place, fp32 / fp64 (generic backward helper)
 void launch_attn_probs(void *S, const void *lse, int dtype, int64_t BH, int64_t Sq, int64_t Skv);

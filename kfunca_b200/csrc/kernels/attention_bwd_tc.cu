@@ -16,6 +16,7 @@
 // gradients (no fp32 atomics on dQ) and two simple pipelines.
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "ew_common.cuh"
 #include "tc_common.cuh"
@@ -432,11 +433,16 @@ static void launch_bwd_mode(const AttnBwdPlan &a, const float *lse2, const float
 bool launch_attention_bwd_tc(const AttnBwdPlan &a) {
     static const bool force_generic = std::getenv("KF_ATTN_BWD_FORCE_GENERIC") != nullptr;
     if (force_generic) return false;
-    // Strided (packed-projection) operands go to the one-kernel scheme; dense ones only with KF_ATTN_BWD_FUSED=1: measured at C3
-    // (profiles/r2_attn_bwd_fused_vs_two.log) the ordered fp32 dQ hand-over through L2 makes it 5.16 ms against 3.42 ms here.
-    static const bool want_fused = std::getenv("KF_ATTN_BWD_FUSED") != nullptr;
-    if ((a.H > 0 || want_fused) && launch_attention_bwd_fused(a)) return true;
-    if (a.H > 0) return false;  // the two-kernel scheme takes dense operands only
+    // Three schemes, all deterministic (profiles/r2_attn_bwd_variants.md has the C3 timings and the pipeline traces):
+    //   two   (this file)                 64-wide tiles, two tile sets, 7 GEMMs; dense operands only.      3.39 ms at C3 — the default for dense
+    //   wide  (attention_bwd_wide.cu)     128-wide tiles, 16 element-wise warps, dense or strided.         3.42 - 3.7 ms — the strided (packed qkv) path
+    //   fused (attention_bwd_fused.cu)    one kernel, 5 GEMMs, ordered fp32 dQ hand-over through L2.       5.16 ms
+    // KF_ATTN_BWD=two|wide|fused forces one (read per call so that tests / A-B runs can flip it).
+    const char *mode = std::getenv("KF_ATTN_BWD");
+    const bool want_fused = mode && std::strcmp(mode, "fused") == 0, want_wide = mode && std::strcmp(mode, "wide") == 0;
+    if (want_fused && launch_attention_bwd_fused(a)) return true;
+    if ((want_wide || a.H > 0) && launch_attention_bwd_wide(a)) return true;
+    if (a.H > 0) return launch_attention_bwd_fused(a);  // strided operands the wide scheme refused (cannot happen for shapes the forward took)
     if (a.dtype != KF_HALF && a.dtype != KF_BFLOAT16) return false;
     if (a.D != 64 && a.D != 128) return false;
     if (a.Sq < 1 || a.Skv < 1 || a.BH < 1 || a.BH >= 65536) return false;

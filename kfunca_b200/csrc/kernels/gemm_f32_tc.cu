@@ -441,7 +441,8 @@ bool launch_gemm_f32_tc(const GemmPlan &g) {
     // below ~ one 128 x 128 x 256 block of work the two extra launches and the 256 x 256 tile granularity lose to the FFMA kernel
     if (g.beta != 0.f && g.alpha == 0.f && g.K > F_KCHUNK) return false;  // beta / alpha is folded into the first K chunk
     const bool forced = mode && (std::strcmp(mode, "x6") == 0 || std::strcmp(mode, "x9") == 0);
-    if (!forced && (g.M < 64 || g.N < 64 || g.K < 32 || (double)g.M * (double)g.N * (double)g.K * (double)g.batch < 128.0 * 128.0 * 256.0)) return false;
+    const int64_t Mr = g.route_M > 0 ? g.route_M : g.M;
+    if (!forced && (Mr < 64 || g.N < 64 || g.K < 32 || (double)Mr * (double)g.N * (double)g.K * (double)g.batch < 128.0 * 128.0 * 256.0)) return false;
     const bool nine = mode && std::strcmp(mode, "x9") == 0;
 #define KF_F32_DISPATCH(NP)                                                        \
     do {                                                                           \

@@ -336,34 +336,35 @@ __global__ void __cluster_dims__(1, CM_C, 1) __launch_bounds__(CM_WARPS * 32) co
     const int64_t r0 = (int64_t)blockIdx.y * CM_WARPS + warp, rstep = (int64_t)CM_C * CM_WARPS;
     if (col_ok) {
         int64_t r = r0;
-        // two rows in flight per thread
-        for (; r + rstep < a.R; r += 2 * rstep) {
-            float v0[VEC], v1[VEC];
-            if (VEC == 4) {
-                const float4 f0 = __ldcs(reinterpret_cast<const float4 *>(base + r * a.inner));
-                const float4 f1 = __ldcs(reinterpret_cast<const float4 *>(base + (r + rstep) * a.inner));
-                v0[0] = f0.x; v0[VEC > 1 ? 1 : 0] = f0.y; v0[VEC > 2 ? 2 : 0] = f0.z; v0[VEC > 3 ? 3 : 0] = f0.w;
-                v1[0] = f1.x; v1[VEC > 1 ? 1 : 0] = f1.y; v1[VEC > 2 ? 2 : 0] = f1.z; v1[VEC > 3 ? 3 : 0] = f1.w;
-            } else {
-                v0[0] = __ldcs(base + r * a.inner);
-                v1[0] = __ldcs(base + (r + rstep) * a.inner);
+        // eight rows in flight per thread: the batch's own mean and centred second moment are formed from registers (two passes, all
+        // independent loads / adds), then folded into the running triple with one Chan update — no per-row dependency chain
+        constexpr int NB = 8;
+        for (; r + (NB - 1) * rstep < a.R; r += NB * rstep) {
+            float v[NB][VEC];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                if (VEC == 4) {
+                    const float4 f = __ldcs(reinterpret_cast<const float4 *>(base + (r + b * rstep) * a.inner));
+                    v[b][0] = f.x; v[b][VEC > 1 ? 1 : 0] = f.y; v[b][VEC > 2 ? 2 : 0] = f.z; v[b][VEC > 3 ? 3 : 0] = f.w;
+                } else {
+                    v[b][0] = __ldcs(base + (r + b * rstep) * a.inner);
+                }
             }
-            n += 1.f;
-            float inv = __frcp_rn(n);
+            const float nn = n + (float)NB, f = (float)NB * __frcp_rn(nn);
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
-                const float d = v0[i] - mean[i];
-                mean[i] = fmaf(d, inv, mean[i]);
-                m2[i] = fmaf(d, v0[i] - mean[i], m2[i]);
-            }
-            n += 1.f;
-            inv = __frcp_rn(n);
+                const float bm = (((v[0][i] + v[1][i]) + (v[2][i] + v[3][i])) + ((v[4][i] + v[5][i]) + (v[6][i] + v[7][i]))) * (1.f / NB);
+                float bs = 0.f;
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                const float d = v1[i] - mean[i];
-                mean[i] = fmaf(d, inv, mean[i]);
-                m2[i] = fmaf(d, v1[i] - mean[i], m2[i]);
+                for (int b = 0; b < NB; ++b) {
+                    const float d = v[b][i] - bm;
+                    bs = fmaf(d, d, bs);
+                }
+                const float d = bm - mean[i];
+                mean[i] = fmaf(d, f, mean[i]);
+                m2[i] = m2[i] + bs + d * d * n * f;
             }
+            n = nn;
         }
         for (; r < a.R; r += rstep) {
             float v0[VEC];

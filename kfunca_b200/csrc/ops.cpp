@@ -764,6 +764,7 @@ struct MatmulGrad : GradFunction {
     std::vector<Tensor> backward(const Tensor &g) override;
 };
 
+static thread_local int64_t g_route_M = 0;  // set by gemm_host around its slab products (GemmPlan::route_M)
 static Tensor matmul_nograd(const Tensor &a, bool ta, const Tensor &b, bool tb, float alpha, float beta, Tensor *out_opt,
                             const Tensor *residual = nullptr) {
     require_device(a, "matmul");
@@ -777,6 +778,7 @@ static Tensor matmul_nograd(const Tensor &a, bool ta, const Tensor &b, bool tb, 
     fill_gemm_operand(b, tb, Kb, p.N, p.ldb, p.sb, batch_b, hb);
     KF_CHECK(Ka == Kb, "matmul: inner dimensions differ (", Ka, " vs ", Kb, ")");
     p.K = Ka;
+    p.route_M = g_route_M;
     std::vector<int64_t> out_shape;
     if (b.dim() == 2 && !ta && a.dim() > 2 && ha.is_contiguous()) {
         // gemm semantics: fold every leading dim of a into M (ref: gemm_kernel.cu:10-15)
@@ -1023,7 +1025,14 @@ void gemm_host(const void *a_host, const void *b_host, void *c_host, int64_t M, 
         if (s >= 2) KF_CUDA(cudaStreamWaitEvent(rt.stream(), c_free[i], 0));  // the download of this C slab's previous tenant is done
         Tensor av = rows == slab_rows ? dA[i] : dA[i].slice(0, 0, rows, 1);
         Tensor cv = rows == slab_rows ? dC[i] : dC[i].slice(0, 0, rows, 1);
-        matmul_nograd(av, false, dB, false, alpha, 0.f, &cv);
+        g_route_M = M;
+        try {
+            matmul_nograd(av, false, dB, false, alpha, 0.f, &cv);
+        } catch (...) {
+            g_route_M = 0;
+            throw;
+        }
+        g_route_M = 0;
         KF_CUDA(cudaEventRecord(a_free[i], rt.stream()));
         KF_CUDA(cudaEventRecord(c_ready[i], rt.stream()));
         KF_CUDA(cudaStreamWaitEvent(down, c_ready[i], 0));
@@ -1267,6 +1276,10 @@ void backward(Tensor &root, const Tensor &grad_output) {
             if (impl->grad) {
                 Tensor &gacc = *impl->grad;
                 run_binary(EW_ADD, gacc, gacc, go);
+            } else if (go.impl.use_count() == 1 && go.impl->storage.use_count() == 1 && !go.impl->storage->external && go.is_contiguous()) {
+                // the incoming gradient is a fresh tensor nobody else can see (its producer's handles are gone): it becomes the leaf's
+                // grad slot as it is — no copy (one read + one write of every parameter- / input-sized gradient per step)
+                impl->grad.reset(new Tensor(go));
             } else {
                 Tensor gcopy = empty(go.sizes(), go.dtype(), go.device());
                 run_copy(gcopy, go);

@@ -1,9 +1,11 @@
 #!/bin/bash
-# bring-up visit for the fused attention backward / strided attention / chunked fp32 GEMM
+# bring-up visit for attention variants: parity + C3 timing per KF_ATTN_BWD mode, then the attention / block tests
 set -u
-tag=$1
+tag=$1; shift
+modes=${*:-wide two}
 mkdir -p gpurun_out
-timeout 300 python tools/gpu_attn.py --parity --bwd > gpurun_out/${tag}_attn.log 2>&1; echo "attn rc=$?"; tail -12 gpurun_out/${tag}_attn.log
-KF_ATTN_BWD_TWO_KERNEL=1 timeout 300 python tools/gpu_attn.py --bwd > gpurun_out/${tag}_attn_two.log 2>&1; echo "attn2 rc=$?"; tail -4 gpurun_out/${tag}_attn_two.log
-timeout 1200 python -m pytest tests/test_attention_gpu.py tests/test_round2_ops_gpu.py tests/test_baseline_shapes_gpu.py tests/test_block_gpu.py -m gpu -q --durations=10 > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?"
-tail -40 gpurun_out/${tag}_pytest.log
+for m in $modes; do
+  KF_ATTN_BWD=$m timeout 300 python tools/gpu_attn.py --parity --bwd > gpurun_out/${tag}_attn_$m.log 2>&1; echo "attn[$m] rc=$?"; tail -8 gpurun_out/${tag}_attn_$m.log
+done
+timeout 1200 python -m pytest tests/test_attention_gpu.py tests/test_baseline_shapes_gpu.py tests/test_block_gpu.py tests/test_gemm_gpu.py -m gpu -q --durations=5 > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?"
+tail -15 gpurun_out/${tag}_pytest.log

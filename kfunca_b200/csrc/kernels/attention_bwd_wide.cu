@@ -125,12 +125,12 @@ __device__ __forceinline__ float2 w_ex2_poly2(float2 x) {
                        __uint_as_float(__float_as_uint(t.y) * 8388608u + __float_as_uint(q.y)));
 }
 
-// Phase A for one thread (one stationary row, 32 streamed columns): P = exp2(T0 c - lse2) into `pr` (fp32, kept for phase B);
-// DKV additionally packs P^T to 16 bits over the first 16 of the 32 TMEM columns just read.
+// Phase A for one thread (one stationary row, 32 streamed columns): P = exp2(T0 c - lse2), rounded to 16 bits, into `pk` (kept for
+// phase B: dS is formed from the SAME rounded P the dV MMA consumes); DKV also stores it over the first 16 of the 32 TMEM columns read.
 // vec_smem (DKV): -lse2 of this thread's 32 streamed columns; nl_row (DQ): -lse2 of this thread's row.
 template <int MODE, bool MASKED, bool BF16>
 __device__ __forceinline__ void w_phase_a(const uint32_t t0_addr, const uint32_t vec_smem, const float nl_row, const float sc, const int lo, const int hi,
-                                          float (&pr)[32], uint64_t *t0_free, long long *tr) {
+                                          uint32_t (&pk)[16], uint64_t *t0_free, long long *tr) {
     const float2 sc2 = make_float2(sc, sc);
     uint32_t s[32];
     tmem_ld32(t0_addr, s);
@@ -157,20 +157,21 @@ __device__ __forceinline__ void w_phase_a(const uint32_t t0_addr, const uint32_t
             if (i + 2 < lo || i + 2 >= hi) p2 = 0.f;
             if (i + 3 < lo || i + 3 >= hi) p3 = 0.f;
         }
-        pr[i] = p0; pr[i + 1] = p1; pr[i + 2] = p2; pr[i + 3] = p3;
+        pk[i >> 1] = w_pack<BF16>(make_float2(p0, p1));
+        pk[(i >> 1) + 1] = w_pack<BF16>(make_float2(p2, p3));
     }
     if (tr) tr[7] = clock64();
-    if (MODE == W_DKV) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = w_pack<BF16>(make_float2(pr[2 * i], pr[2 * i + 1]));
-        tmem_st16(t0_addr, pk);
-    }
+    if (MODE == W_DKV) tmem_st16(t0_addr, pk);
 }
 
 // Phase B: dS = P o (T1 - delta) -> 16 bits over the first 16 of the 32 TMEM columns of T1 this thread has just read.
+template <bool BF16>
+__device__ __forceinline__ float2 w_unpack(uint32_t v) {
+    if (BF16) return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+    return __half22float2(*reinterpret_cast<const __half2 *>(&v));
+}
 template <int MODE, bool BF16>
-__device__ __forceinline__ void w_phase_b(const uint32_t t1_addr, const uint32_t ds_addr, const uint32_t vec_smem, const float nd_row, const float (&pr)[32],
+__device__ __forceinline__ void w_phase_b(const uint32_t t1_addr, const uint32_t ds_addr, const uint32_t vec_smem, const float nd_row, const uint32_t (&pk)[16],
                                           uint64_t *t1_free, uint64_t *ds_free, const uint32_t ds_free_parity, long long *tr) {
     uint32_t d[32];
     tmem_ld32(t1_addr, d);
@@ -187,9 +188,9 @@ __device__ __forceinline__ void w_phase_b(const uint32_t t1_addr, const uint32_t
         float4 nd;
         if (MODE == W_DKV) nd = w_lds128(vec_smem + 4u * i);
         else nd = make_float4(nd_row, nd_row, nd_row, nd_row);
-        const float2 da = __fmul2_rn(make_float2(pr[i], pr[i + 1]),
+        const float2 da = __fmul2_rn(w_unpack<BF16>(pk[i >> 1]),
                                      __fadd2_rn(make_float2(__uint_as_float(d[i]), __uint_as_float(d[i + 1])), make_float2(nd.x, nd.y)));
-        const float2 db = __fmul2_rn(make_float2(pr[i + 2], pr[i + 3]),
+        const float2 db = __fmul2_rn(w_unpack<BF16>(pk[(i >> 1) + 1]),
                                      __fadd2_rn(make_float2(__uint_as_float(d[i + 2]), __uint_as_float(d[i + 3])), make_float2(nd.z, nd.w)));
         dk[i >> 1] = w_pack<BF16>(da);
         dk[(i >> 1) + 1] = w_pack<BF16>(db);
@@ -448,7 +449,7 @@ attn_bwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_c
             nl_row = p.nlse2[(int64_t)bh * p.Sq_pad + row_g];
             nd_row = p.ndelta[(int64_t)bh * p.Sq_pad + row_g];
         }
-        float pr[32];
+        uint32_t pk[16];
         for (int n = 0; n < ntile; ++n) {
             const int64_t y0_row = (int64_t)(t_lo + n) * 128;
             const int sv = n & 1;
@@ -474,11 +475,11 @@ attn_bwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_c
             tc_fence_after();
             if (warp == 0) W_TRACE(n, 2);
             if (p.is_bf16) {
-                if (need_mask) w_phase_a<MODE, true, true>(t0_addr, vl, nl_row, sc, lo, hi, pr, p_full, tr);
-                else w_phase_a<MODE, false, true>(t0_addr, vl, nl_row, sc, lo, hi, pr, p_full, tr);
+                if (need_mask) w_phase_a<MODE, true, true>(t0_addr, vl, nl_row, sc, lo, hi, pk, p_full, tr);
+                else w_phase_a<MODE, false, true>(t0_addr, vl, nl_row, sc, lo, hi, pk, p_full, tr);
             } else {
-                if (need_mask) w_phase_a<MODE, true, false>(t0_addr, vl, nl_row, sc, lo, hi, pr, p_full, tr);
-                else w_phase_a<MODE, false, false>(t0_addr, vl, nl_row, sc, lo, hi, pr, p_full, tr);
+                if (need_mask) w_phase_a<MODE, true, false>(t0_addr, vl, nl_row, sc, lo, hi, pk, p_full, tr);
+                else w_phase_a<MODE, false, false>(t0_addr, vl, nl_row, sc, lo, hi, pk, p_full, tr);
             }
             if (MODE == W_DKV) {
                 tmem_st_wait();
@@ -494,8 +495,8 @@ attn_bwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_c
             if (warp == 0) W_TRACE(n, 4);
             const uint32_t ds_addr = MODE == W_DKV ? t1_addr : ds_base + (uint32_t)((n & 1) * 64);
             const uint32_t dsf_par = (uint32_t)(((n >> 1) & 1) ^ 1);
-            if (p.is_bf16) w_phase_b<MODE, true>(t1_addr, ds_addr, vd, nd_row, pr, t1_free, &ds_free[n & 1], dsf_par, tr);
-            else w_phase_b<MODE, false>(t1_addr, ds_addr, vd, nd_row, pr, t1_free, &ds_free[n & 1], dsf_par, tr);
+            if (p.is_bf16) w_phase_b<MODE, true>(t1_addr, ds_addr, vd, nd_row, pk, t1_free, &ds_free[n & 1], dsf_par, tr);
+            else w_phase_b<MODE, false>(t1_addr, ds_addr, vd, nd_row, pk, t1_free, &ds_free[n & 1], dsf_par, tr);
             tmem_st_wait();
             if (tr) tr[15] = clock64();
             tc_fence_before();

@@ -184,6 +184,105 @@ __device__ __forceinline__ void fwd_softmax_block(const uint32_t s_addr, const u
     l_run += (rs2.x + rs2.y) + (rs3.x + rs3.y);
 }
 
+// Two threads per query row WITHOUT a barrier in front of the exponentials (KF_ATTN_SPLIT=2).  Each thread owns 64 of the 128 keys of
+// the block.  It takes its exponentials relative to a reference it knows on its own: the running reference m_ref, or — when its own
+// 64-key maximum exceeds m_ref by more than 2^8 (always in the first block) — that maximum.  The two halves of a row exchange their
+// maxima through shared memory AFTER P has been stored (one 64-thread named barrier, normally already satisfied), agree on the new
+// reference, and only in the rare case that a thread's own reference differs from it rescale their stored 16-bit P (a factor <= 1) and,
+// when the reference moved, O and l.  Every intermediate stays finite: P <= 2^8 relative to m_ref, <= 1 relative to an own maximum.
+// P of keys [0, 64) lands on TMEM columns [0, 32) of the tile's S region and P of keys [64, 128) on [64, 96): a thread only overwrites
+// S columns it has read itself.  POLY of every 8 column pairs take the FMA-pipe exp2.
+template <int D, bool BF16, bool MASKED, int POLY>
+__device__ __forceinline__ void fwd_softmax_block_split(const uint32_t s_addr, const uint32_t o_addr, const float sc, const int lim, const bool first,
+                                                        float &m_ref, float &l_run, float *xch_mine, const float *xch_peer, const int bar_id,
+                                                        uint64_t *p_bar) {
+    uint32_t s[2][32];
+    tmem_ld32(s_addr, s[0]);
+    tmem_ld32(s_addr + 32, s[1]);
+    tmem_ld_wait();
+    if (MASKED) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (c * 32 + i > lim) s[c][i] = 0xff800000u;  // -inf
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+            mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
+            mx1 = fmaxf(mx1, fmaxf(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])));
+            mx2 = fmaxf(mx2, fmaxf(__uint_as_float(s[c][i + 4]), __uint_as_float(s[c][i + 5])));
+            mx3 = fmaxf(mx3, fmaxf(__uint_as_float(s[c][i + 6]), __uint_as_float(s[c][i + 7])));
+        }
+    const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;  // this half's maximum in the exp2 domain
+    *xch_mine = mx;
+    const float r_own = (mx > m_ref + 8.f) ? mx : m_ref;  // m_ref = -inf in the first block: then the own maximum (or -inf when fully masked)
+    const float m_use = (r_own == -INFINITY) ? 0.f : r_own;
+    const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(-m_use, -m_use);
+    float2 rs2 = make_float2(0.f, 0.f), rs3 = make_float2(0.f, 0.f);
+    uint32_t pk[32];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
+            if (((i >> 1) & 7) < POLY) {
+                x = ex2_poly2(x);
+            } else {
+                x.x = ex2_approx(x.x);
+                x.y = ex2_approx(x.y);
+            }
+            if (i & 2) rs3 = __fadd2_rn(rs3, x);
+            else rs2 = __fadd2_rn(rs2, x);
+            pk[c * 16 + (i >> 1)] = pack16t<BF16>(x);
+        }
+    tmem_st32(s_addr, pk);  // over this thread's own S columns [0, 32) of its 64
+    float rs = (rs2.x + rs2.y) + (rs3.x + rs3.y);
+    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+    const float m_blk = fmaxf(mx, *xch_peer);
+    const bool grow = m_blk > m_ref + 8.f;
+    const float m_new = grow ? m_blk : m_ref;  // m_blk > m_ref whenever grow
+    const bool fix = r_own != m_new;           // this thread's exponentials used another reference than the row's new one
+    if (__any_sync(0xffffffffu, fix)) {
+        const float f = fix ? ((r_own == -INFINITY) ? 0.f : ex2_approx(r_own - m_new)) : 1.f;
+        rs *= f;
+        tmem_st_wait();
+        uint32_t q[32];
+        tmem_ld32(s_addr, q);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            float2 v;
+            if (BF16) v = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&q[i]));
+            else v = __half22float2(*reinterpret_cast<__half2 *>(&q[i]));
+            q[i] = pack16t<BF16>(make_float2(v.x * f, v.y * f));
+        }
+        tmem_st32(s_addr, q);
+    }
+    if (!first && __any_sync(0xffffffffu, grow)) {
+        const float f = grow ? ((m_ref == -INFINITY) ? 0.f : ex2_approx(m_ref - m_new)) : 1.f;
+        l_run *= f;
+#pragma unroll 1
+        for (int c = 0; c < D / 64; ++c) {
+            uint32_t orr[32];
+            tmem_ld32(o_addr + (uint32_t)(c * 32), orr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * f);
+            tmem_st32(o_addr + (uint32_t)(c * 32), orr);
+        }
+    }
+    m_ref = m_new;
+    l_run += rs;
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(p_bar);
+}
+
 // One CTA = two 128-row query tiles (a 256-row "pair") of one (batch, head); the two tiles ping-pong on the
 // tensor pipe: while softmax warps work on S of tile t, the MMA warp runs P V + the next Q K^T of tile 1-t.
 // Warp roles: [0, 8 NH) softmax (tile = w / (4 NH), column half = (w / 4) % NH, TMEM lane quarter = w % 4), then the MMA issuer,
@@ -304,7 +403,8 @@ __device__ __forceinline__ void attn_fwd_tc_body(const CUtensorMap &tmap_q, cons
                 for (int kk = half * (FA_BKV / 32); kk < (half + 1) * (FA_BKV / 32); ++kk) {
                     // A = P from tensor memory: 16 k-values of 16 bits = 8 columns per step;
                     // B = V, MN-major: 16 kv rows = 2 x 1024 B per step, 64-wide d atoms ATOM_BYTES apart
-                    umma_f16_ts_p(tmem_base + O_COL + (uint32_t)(t * D), tmem_base + (uint32_t)(t * 128 + kk * 8),
+                    const uint32_t pcol = NH == 1 ? (uint32_t)(kk * 8) : (uint32_t)((kk >> 2) * 64 + (kk & 3) * 8);  // NH = 2: P halves at columns 0 / 64
+                    umma_f16_ts_p(tmem_base + O_COL + (uint32_t)(t * D), tmem_base + (uint32_t)(t * 128) + pcol,
                                   make_sw128_desc(v_addr + kk * 2048, ATOM_BYTES, 1024), idesc_pv, (accumulate || kk) ? 1u : 0u, leader);
                 }
             };
@@ -385,7 +485,15 @@ __device__ __forceinline__ void attn_fwd_tc_body(const CUtensorMap &tmap_q, cons
                 uint64_t *p_bar = &p_full[2 * t + h];  // NH = 1: halves 0 and 1 in turn; NH = 2: this warp's half
                 float *xm_j = xm + (j & 1) * 128;
                 const float *xp_j = xp + (j & 1) * 128;
-                if (p.is_bf16) {
+                if constexpr (NH == 2) {
+                    if (p.is_bf16) {
+                        if (masked) fwd_softmax_block_split<D, true, true, POLY>(s_addr, o_addr, sc, lim, j == 0, m_ref, l_run, xm_j, xp_j, bar_id, p_bar);
+                        else fwd_softmax_block_split<D, true, false, POLY>(s_addr, o_addr, sc, lim, j == 0, m_ref, l_run, xm_j, xp_j, bar_id, p_bar);
+                    } else {
+                        if (masked) fwd_softmax_block_split<D, false, true, POLY>(s_addr, o_addr, sc, lim, j == 0, m_ref, l_run, xm_j, xp_j, bar_id, p_bar);
+                        else fwd_softmax_block_split<D, false, false, POLY>(s_addr, o_addr, sc, lim, j == 0, m_ref, l_run, xm_j, xp_j, bar_id, p_bar);
+                    }
+                } else if (p.is_bf16) {
                     if (masked) fwd_softmax_block<D, true, true, POLY, NH>(s_addr, p_addr, o_addr, sc, lim, j == 0, m_ref, l_run, xm_j, xp_j, bar_id, p_bar);
                     else fwd_softmax_block<D, true, false, POLY, NH>(s_addr, p_addr, o_addr, sc, lim, j == 0, m_ref, l_run, xm_j, xp_j, bar_id, p_bar);
                 } else {

@@ -287,7 +287,6 @@ def run_ours(args):
         out["config"]["configs"] = cfgs
         out["config"]["reference_build"] = (ref_cfg or {}).get("_meta", {"unavailable": "not run"})
         out["roofline"]["per_config"] = {c["name"]: c["roofline"]["frac"] for c in cfgs if c.get("roofline")}
-        out["extras"] = {c["name"]: c for c in cfgs}  # kept under the old key as well
     if block_res is not None:
         out["config"]["c5_block"] = block_res
         out["extras"] = {"c5_block": block_res}

@@ -58,6 +58,10 @@ int kf_get_device(int *device);
 /* The library's single compute stream as a cudaStream_t value (non-default, non-blocking). */
 int kf_stream(void **cuda_stream);
 int kf_synchronize(void);
+/* `t`'s memory is also used by work enqueued on `stream` (a cudaStream_t other than the library's, e.g. the stream of a framework holding
+ * a zero-copy alias): when the storage is released the library stream first waits for that stream (replaces the hand-placed joins the
+ * reference's single implicit stream never needed, launcher_cuda.h:113-116).  No-op for the library stream itself. */
+int kf_record_stream(kf_tensor_t t, void *stream);
 /* Human-readable device table. ref: device_info(), src/device/device_info.cu:191-216 */
 int kf_device_info(char *buf, size_t buf_len);
 /* Pool statistics. ref: DeviceAllocator::print, src/core/device_allocator.cpp:17-35 */
@@ -248,6 +252,10 @@ int kf_promote_types(int a, int b, int *out);
  * the block returned by op number (-ops[i]-1). offsets[i] receives the fake address (or -1 for frees);
  * stats = {bytes_in_use, bytes_reserved, n_arena_mallocs}. */
 int kf_debug_pool_trace(const int64_t *ops, int n, int64_t *offsets, int64_t *stats3);
+/* the same fake pool with side streams: kind[i] 0 = allocate arg[i] bytes, 1 = release the block of op arg[i], 2 = record that stream
+ * id arg2[i] uses the block of op arg[i].  fence_log receives, in order, the stream id of every fence the pool issues while releasing
+ * (capacity cap); *nfences = how many it issued. */
+int kf_debug_pool_fences(const int *kind, const int64_t *arg, const int64_t *arg2, int n, int64_t *fence_log, int cap, int *nfences);
 
 #ifdef __cplusplus
 }

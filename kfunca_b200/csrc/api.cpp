@@ -668,6 +668,48 @@ void *fake_alloc(size_t bytes, void *ctx) {
 void fake_free(void *, void *) {}
 }  // namespace
 
+struct FenceLog {
+    FakeArena arena;
+    std::vector<int64_t> log;
+};
+static void *fl_alloc(size_t bytes, void *ctx) { return fake_alloc(bytes, &static_cast<FenceLog *>(ctx)->arena); }
+static void fl_free(void *p, void *ctx) { fake_free(p, &static_cast<FenceLog *>(ctx)->arena); }
+static void fl_fence(void *stream, void *ctx) { static_cast<FenceLog *>(ctx)->log.push_back((int64_t)(intptr_t)stream); }
+
+int kf_debug_pool_fences(const int *kind, const int64_t *arg, const int64_t *arg2, int n, int64_t *fence_log, int cap, int *nfences) {
+    KF_API_BEGIN
+    FenceLog fl;
+    {
+        Pool pool(fl_alloc, fl_free, &fl, fl_fence);
+        std::vector<void *> ptrs(n, nullptr);
+        for (int i = 0; i < n; ++i) {
+            if (kind[i] == 0) {
+                ptrs[i] = pool.allocate((size_t)arg[i]);
+            } else {
+                const int64_t j = arg[i];
+                KF_CHECK(j >= 0 && j < i && ptrs[j], "pool fence trace: bad target");
+                if (kind[i] == 1) {
+                    pool.release(ptrs[j]);
+                    ptrs[j] = nullptr;
+                } else {
+                    pool.record_stream((char *)ptrs[j] + 1, (void *)(intptr_t)arg2[i]);  // an interior address finds its block
+                }
+            }
+        }
+    }
+    *nfences = (int)fl.log.size();
+    for (int i = 0; i < (int)fl.log.size() && i < cap; ++i) fence_log[i] = fl.log[i];
+    KF_API_END
+}
+
+int kf_record_stream(kf_tensor_t t, void *stream) {
+    KF_API_BEGIN
+    const Tensor &x = T(t);
+    KF_CHECK(x.defined() && !x.is_meta(), "record_stream needs a device tensor");
+    if (!x.impl->storage->external && stream != (void *)Runtime::get().stream()) Runtime::get().pool().record_stream(x.impl->storage->ptr, stream);
+    KF_API_END
+}
+
 int kf_debug_pool_trace(const int64_t *ops_, int n, int64_t *offsets, int64_t *stats3) {
     KF_API_BEGIN
     FakeArena arena;

@@ -107,6 +107,7 @@ void grad_hook(const Tensor &leaf, const Tensor &grad, void *) {
     // the comm stream starts this collective once the kernels that produced the gradient (already on the library stream) are done
     KF_CUDA(cudaEventRecord(g.ev_grad, rt.stream()));
     KF_CUDA(cudaStreamWaitEvent(g.comm_stream, g.ev_grad, 0));
+    rt.pool().record_stream(grad.data(), g.comm_stream);  // a gradient dropped before dist_overlap_end() is fenced by the pool
     KF_NCCL(api().AllReduce(grad.data(), grad.data(), (size_t)grad.numel(), nccl_dtype(grad.dtype()), ncclAvg, g.comm, g.comm_stream));
     ++g.hook_calls;
     g.bytes += grad.numel() * (int64_t)grad.itemsize();

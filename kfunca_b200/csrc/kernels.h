@@ -146,7 +146,7 @@ void launch_layer_norm_fwd(const void *x, const void *gain, void *y, float *mean
 // one-launch column statistics over [outer, R, inner] fp32 (kernels/norm.cu): mode 0 = norm_stat (mean, invstd), mode 1 = mean_var
 bool launch_col_moments(const void *x, void *out0, void *out1, int dtype, int64_t outer, int64_t R, int64_t inner, int mode, bool take_sqrt,
                         double eps);
-int layer_norm_bwd_ctas(int64_t rows);
+int layer_norm_bwd_ctas(int64_t rows, bool write_dx);
 // mean + unbiased variance (or its sqrt) of each dense fp32 row in ONE pass; false when the shape is not covered
 bool launch_row_moments(const void *x, void *mean, void *var, int dtype, int64_t rows, int64_t E, bool take_sqrt);
 void launch_layer_norm_bwd(const void *x, const void *gain, const void *dy, const float *mean, const float *rstd, void *dx,

@@ -16,6 +16,9 @@
 //             ordinary column reduction folds afterwards: deterministic, no atomics.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "ew_common.cuh"
 
 namespace kf {
@@ -28,11 +31,13 @@ __device__ __forceinline__ float ln_warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-// sum over the 128 threads of the CTA, result in every thread; `slot` = 4 floats of shared memory not in use by another sum
+// sum over the TH (128 or 256) threads of the CTA, result in every thread; `slot` = TH / 32 floats of shared memory not in use by another sum
+template <int TH = LN_THREADS>
 __device__ __forceinline__ float ln_block_sum(float v, float *slot) {
     v = ln_warp_sum(v);
     if ((threadIdx.x & 31) == 0) slot[threadIdx.x >> 5] = v;
     __syncthreads();
+    if (TH == 256) return ((slot[0] + slot[1]) + (slot[2] + slot[3])) + ((slot[4] + slot[5]) + (slot[6] + slot[7]));
     return (slot[0] + slot[1]) + (slot[2] + slot[3]);
 }
 
@@ -51,9 +56,11 @@ struct LnArgs {
     int rms;                 // 1 = RMSNorm (README.md:28 `rms_norm`): no centring, rstd = 1 / sqrt(mean(x^2) + eps), mean stored as 0
 };
 
-template <typename T, int VEC, int NV>
-__global__ void __launch_bounds__(LN_THREADS) layer_norm_fwd_kernel(const LnArgs a) {
-    __shared__ float red[8];
+// TH threads per row: 128, or 256 for rows that would need 8 vectors per thread at 128 (E = 4096 fp32: 55 -> 32 registers, 47 % -> full
+// occupancy, more loads in flight per SM)
+template <typename T, int VEC, int NV, int TH>
+__global__ void __launch_bounds__(TH) layer_norm_fwd_kernel(const LnArgs a) {
+    __shared__ float red[16];
     const int64_t row = blockIdx.x;
     const int nvec = (int)(a.E / VEC);
     const T *__restrict__ x = reinterpret_cast<const T *>(a.x) + row * a.E;
@@ -61,7 +68,7 @@ __global__ void __launch_bounds__(LN_THREADS) layer_norm_fwd_kernel(const LnArgs
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-        const int iv = threadIdx.x + k * LN_THREADS;
+        const int iv = threadIdx.x + k * TH;
         if (iv < nvec) {
             const Pack<T, VEC> pk = ln_ld<T, VEC>(x + (int64_t)iv * VEC);
 #pragma unroll
@@ -71,11 +78,11 @@ __global__ void __launch_bounds__(LN_THREADS) layer_norm_fwd_kernel(const LnArgs
             }
         }
     }
-    const float mean = a.rms ? 0.f : ln_block_sum(s, red) / (float)a.E;  // a.rms is uniform over the grid: no divergent barrier
+    const float mean = a.rms ? 0.f : ln_block_sum<TH>(s, red) / (float)a.E;  // a.rms is uniform over the grid: no divergent barrier
     float d = 0.f;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-        const int iv = threadIdx.x + k * LN_THREADS;
+        const int iv = threadIdx.x + k * TH;
         if (iv < nvec) {
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
@@ -84,7 +91,7 @@ __global__ void __launch_bounds__(LN_THREADS) layer_norm_fwd_kernel(const LnArgs
             }
         }
     }
-    const float rstd = rsqrtf(ln_block_sum(d, red + 4) / (float)a.E + a.eps);
+    const float rstd = rsqrtf(ln_block_sum<TH>(d, red + 8) / (float)a.E + a.eps);
     if (threadIdx.x == 0) {
         a.mean[row] = mean;
         a.rstd[row] = rstd;
@@ -93,7 +100,7 @@ __global__ void __launch_bounds__(LN_THREADS) layer_norm_fwd_kernel(const LnArgs
     T *__restrict__ y = reinterpret_cast<T *>(a.y) + row * a.E;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-        const int iv = threadIdx.x + k * LN_THREADS;
+        const int iv = threadIdx.x + k * TH;
         if (iv < nvec) {
             const Pack<T, VEC> gk = ln_ld<T, VEC>(g + (int64_t)iv * VEC);
             Pack<T, VEC> out;
@@ -106,10 +113,10 @@ __global__ void __launch_bounds__(LN_THREADS) layer_norm_fwd_kernel(const LnArgs
 
 // Row statistics only (mean_var over the last dimension, ref: gpu::mean_var, src/core/reduce_ops.cpp:22-28 — Welford with
 // correction 1): same register-resident two-pass scheme, one HBM read; out_var = M2 / (E - 1), optionally its square root.
-template <typename T, int VEC, int NV>
-__global__ void __launch_bounds__(LN_THREADS) row_moments_kernel(const T *__restrict__ xin, T *__restrict__ out_mean, T *__restrict__ out_var,
+template <typename T, int VEC, int NV, int TH>
+__global__ void __launch_bounds__(TH) row_moments_kernel(const T *__restrict__ xin, T *__restrict__ out_mean, T *__restrict__ out_var,
                                                                  const int64_t E, const int take_sqrt) {
-    __shared__ float red[8];
+    __shared__ float red[16];
     const int64_t row = blockIdx.x;
     const int nvec = (int)(E / VEC);
     const T *__restrict__ x = xin + row * E;
@@ -117,7 +124,7 @@ __global__ void __launch_bounds__(LN_THREADS) row_moments_kernel(const T *__rest
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-        const int iv = threadIdx.x + k * LN_THREADS;
+        const int iv = threadIdx.x + k * TH;
         if (iv < nvec) {
             const Pack<T, VEC> pk = ln_ld<T, VEC>(x + (int64_t)iv * VEC);
 #pragma unroll
@@ -127,17 +134,17 @@ __global__ void __launch_bounds__(LN_THREADS) row_moments_kernel(const T *__rest
             }
         }
     }
-    const float mean = ln_block_sum(s, red) / (float)E;
+    const float mean = ln_block_sum<TH>(s, red) / (float)E;
     float d = 0.f;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-        const int iv = threadIdx.x + k * LN_THREADS;
+        const int iv = threadIdx.x + k * TH;
         if (iv < nvec) {
 #pragma unroll
             for (int i = 0; i < VEC; ++i) d += (v[k][i] - mean) * (v[k][i] - mean);
         }
     }
-    const float m2 = ln_block_sum(d, red + 4);
+    const float m2 = ln_block_sum<TH>(d, red + 8);
     if (threadIdx.x == 0) {
         const float div = (float)E - 1.f;
         float var = m2 / (div > 0.f ? div : 0.f);
@@ -232,6 +239,109 @@ __global__ void __launch_bounds__(LN_THREADS) layer_norm_bwd_kernel(const LnArgs
     }
 }
 
+// One-pass backward: dx AND the gain-gradient partials from a single read of x and dy.  Persistent CTAs (two per SM) stride over the
+// rows; a thread keeps the gain-gradient sums of its columns in registers, and the NEXT row's x / dy vectors are already in flight
+// (raw, in registers) while the current row goes through its one barrier and its store — the load -> barrier -> store serialisation
+// that made the first one-kernel version slow (303 us at [32768, 4096] bf16) is gone.  Against the two-launch form this saves the
+// second read of x and dy (2/5 of the bytes).
+template <typename T, int VEC, int NV>
+__global__ void __launch_bounds__(LN_THREADS, 2) layer_norm_bwd_fused_kernel(const LnArgs a) {
+    __shared__ float red[2][8];
+    const int nvec = (int)(a.E / VEC);
+    const T *__restrict__ gp = reinterpret_cast<const T *>(a.gain);
+    float dgain[NV][VEC];
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) dgain[k][i] = 0.f;
+    Pack<T, VEC> xk[NV], dk[NV];
+    float mean = 0.f, rstd = 0.f;
+    auto fetch = [&](int64_t row, Pack<T, VEC>(&xo)[NV], Pack<T, VEC>(&dO)[NV], float &m, float &r) {
+        const T *__restrict__ x = reinterpret_cast<const T *>(a.x) + row * a.E;
+        const T *__restrict__ dy = reinterpret_cast<const T *>(a.dy) + row * a.E;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int iv = threadIdx.x + k * LN_THREADS;
+            if (iv < nvec) {
+                xo[k] = ln_ld<T, VEC>(x + (int64_t)iv * VEC);
+                dO[k] = ln_ld<T, VEC>(dy + (int64_t)iv * VEC);
+            }
+        }
+        m = a.mean[row];
+        r = a.rstd[row];
+    };
+    int64_t row = blockIdx.x;
+    if (row < a.rows) fetch(row, xk, dk, mean, rstd);
+    int it = 0;
+    for (; row < a.rows; row += gridDim.x, ++it) {
+        Pack<T, VEC> xn[NV], dn[NV];
+        float mean_n = 0.f, rstd_n = 0.f;
+        const int64_t next = row + gridDim.x;
+        if (next < a.rows) fetch(next, xn, dn, mean_n, rstd_n);
+        // pass 1 over the registers: row sums and the gain-gradient terms (x-hat and dy * gain are NOT kept: the raw vectors are, and
+        // pass 2 recomputes them — four register arrays per thread would spill at E = 4096 fp32)
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int iv = threadIdx.x + k * LN_THREADS;
+            if (iv < nvec) {
+                const Pack<T, VEC> gk = ln_ld<T, VEC>(gp + (int64_t)iv * VEC);  // 16 KB at most, L1-resident after the first row
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const float g = cvt_in<float>(dk[k].v[i]);
+                    const float xh = (cvt_in<float>(xk[k].v[i]) - mean) * rstd;
+                    const float gg = g * cvt_in<float>(gk.v[i]);
+                    dgain[k][i] += g * xh;
+                    s1 += gg;
+                    s2 += gg * xh;
+                }
+            }
+        }
+        float *slot = red[it & 1];
+        s1 = ln_warp_sum(s1);
+        s2 = ln_warp_sum(s2);
+        if ((threadIdx.x & 31) == 0) {
+            slot[threadIdx.x >> 5] = s1;
+            slot[4 + (threadIdx.x >> 5)] = s2;
+        }
+        __syncthreads();
+        const float c1 = a.rms ? 0.f : ((slot[0] + slot[1]) + (slot[2] + slot[3])) / (float)a.E;
+        const float c2 = ((slot[4] + slot[5]) + (slot[6] + slot[7])) / (float)a.E;
+        T *__restrict__ dx = reinterpret_cast<T *>(a.dx) + row * a.E;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int iv = threadIdx.x + k * LN_THREADS;
+            if (iv < nvec) {
+                const Pack<T, VEC> gk = ln_ld<T, VEC>(gp + (int64_t)iv * VEC);
+                Pack<T, VEC> out;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const float xh = (cvt_in<float>(xk[k].v[i]) - mean) * rstd;
+                    const float gg = cvt_in<float>(dk[k].v[i]) * cvt_in<float>(gk.v[i]);
+                    out.v[i] = cvt_out<T, float>(rstd * (gg - c1 - xh * c2));
+                }
+                *reinterpret_cast<Pack<T, VEC> *>(dx + (int64_t)iv * VEC) = out;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            xk[k] = xn[k];
+            dk[k] = dn[k];
+        }
+        mean = mean_n;
+        rstd = rstd_n;
+    }
+    float *__restrict__ part = a.dgain_partial + (int64_t)blockIdx.x * a.E;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int iv = threadIdx.x + k * LN_THREADS;
+        if (iv < nvec) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) part[(int64_t)iv * VEC + i] = dgain[k][i];
+        }
+    }
+}
+
 template <typename T>
 static int ln_nv(int64_t E) {
     constexpr int VEC = 16 / sizeof(T);
@@ -255,10 +365,10 @@ static void ln_fwd_typed(const LnArgs &a) {
     KF_CHECK(a.rows < (int64_t)0x7FFFFFFF);
     const unsigned grid = (unsigned)a.rows;
     switch (ln_nv<T>(a.E)) {
-    case 1: layer_norm_fwd_kernel<T, VEC, 1><<<grid, LN_THREADS, 0, rt.stream()>>>(a); break;
-    case 2: layer_norm_fwd_kernel<T, VEC, 2><<<grid, LN_THREADS, 0, rt.stream()>>>(a); break;
-    case 4: layer_norm_fwd_kernel<T, VEC, 4><<<grid, LN_THREADS, 0, rt.stream()>>>(a); break;
-    default: layer_norm_fwd_kernel<T, VEC, 8><<<grid, LN_THREADS, 0, rt.stream()>>>(a); break;
+    case 1: layer_norm_fwd_kernel<T, VEC, 1, LN_THREADS><<<grid, LN_THREADS, 0, rt.stream()>>>(a); break;
+    case 2: layer_norm_fwd_kernel<T, VEC, 2, LN_THREADS><<<grid, LN_THREADS, 0, rt.stream()>>>(a); break;
+    case 4: layer_norm_fwd_kernel<T, VEC, 4, LN_THREADS><<<grid, LN_THREADS, 0, rt.stream()>>>(a); break;
+    default: layer_norm_fwd_kernel<T, VEC, 4, 256><<<grid, 256, 0, rt.stream()>>>(a); break;  // 8 vectors per thread at 128 = 4 at 256
     }
     rt.post_launch("layer_norm_fwd_kernel");
 }
@@ -283,10 +393,10 @@ bool launch_row_moments(const void *x, void *mean, void *var, int dtype, int64_t
     float *mp = reinterpret_cast<float *>(mean), *vp = reinterpret_cast<float *>(var);
     const unsigned grid = (unsigned)rows;
     switch (ln_nv<float>(E)) {
-    case 1: row_moments_kernel<float, 4, 1><<<grid, LN_THREADS, 0, rt.stream()>>>(xp, mp, vp, E, take_sqrt); break;
-    case 2: row_moments_kernel<float, 4, 2><<<grid, LN_THREADS, 0, rt.stream()>>>(xp, mp, vp, E, take_sqrt); break;
-    case 4: row_moments_kernel<float, 4, 4><<<grid, LN_THREADS, 0, rt.stream()>>>(xp, mp, vp, E, take_sqrt); break;
-    default: row_moments_kernel<float, 4, 8><<<grid, LN_THREADS, 0, rt.stream()>>>(xp, mp, vp, E, take_sqrt); break;
+    case 1: row_moments_kernel<float, 4, 1, LN_THREADS><<<grid, LN_THREADS, 0, rt.stream()>>>(xp, mp, vp, E, take_sqrt); break;
+    case 2: row_moments_kernel<float, 4, 2, LN_THREADS><<<grid, LN_THREADS, 0, rt.stream()>>>(xp, mp, vp, E, take_sqrt); break;
+    case 4: row_moments_kernel<float, 4, 4, LN_THREADS><<<grid, LN_THREADS, 0, rt.stream()>>>(xp, mp, vp, E, take_sqrt); break;
+    default: row_moments_kernel<float, 4, 4, 256><<<grid, 256, 0, rt.stream()>>>(xp, mp, vp, E, take_sqrt); break;
     }
     rt.post_launch("row_moments_kernel");
     return true;
@@ -302,7 +412,7 @@ bool launch_row_moments(const void *x, void *mean, void *var, int dtype, int64_t
 // row shared by its VEC columns), the 8 warps merge through shared memory (Chan's pairwise update, fixed order), the CTAs merge
 // through distributed shared memory in rank order: deterministic, no atomics, no staging buffer, no semaphore (the reference's
 // un-zeroed semaphore block, SURVEY F10, has no counterpart).
-constexpr int CM_C = 8, CM_WARPS = 8;
+constexpr int CM_C = 8, CM_WARPS = 16;  // 16 warps: half as many rows per thread, twice the loads in flight per SM (ncu: 22 % occupancy at 8)
 
 struct ColMomentsArgs {
     const float *x;
@@ -470,8 +580,13 @@ bool launch_col_moments(const void *x, void *out0, void *out1, int dtype, int64_
     return true;
 }
 
-int layer_norm_bwd_ctas(int64_t rows) {
-    const int64_t cap = (int64_t)Runtime::get().props().sm_count * 8;  // 8 CTAs of 128 threads per SM keep enough loads in flight
+int layer_norm_bwd_ctas(int64_t rows, bool write_dx) {
+    // gain gradient only: 8 CTAs of 128 threads per SM keep enough loads in flight (no barrier, no store in the row loop);
+    // dx + gain gradient in one pass: two resident CTAs per SM (register budget), each with the next row's loads in flight.
+    // KF_LN_BWD=two keeps the two-launch form (A/B runs).
+    const char *mode = std::getenv("KF_LN_BWD");
+    const bool two = mode && std::strcmp(mode, "two") == 0;
+    const int64_t cap = (int64_t)Runtime::get().props().sm_count * ((write_dx && !two) ? 2 : 8);
     return (int)std::max<int64_t>(1, std::min<int64_t>(rows, cap));
 }
 
@@ -479,8 +594,14 @@ template <typename T>
 static void ln_bwd_typed(const LnArgs &a, int ctas, bool write_dx) {
     constexpr int VEC = 16 / sizeof(T);
     Runtime &rt = Runtime::get();
+    const char *mode = std::getenv("KF_LN_BWD");
+    const bool two = mode && std::strcmp(mode, "two") == 0;
 #define KF_LN_BWD(NVV)                                                                                                          \
     do {                                                                                                                        \
+        if (write_dx && !two) {                                                                                                 \
+            layer_norm_bwd_fused_kernel<T, VEC, NVV><<<ctas, LN_THREADS, 0, rt.stream()>>>(a);                                  \
+            break;                                                                                                              \
+        }                                                                                                                       \
         if (write_dx) {                                                                                                         \
             layer_norm_bwd_kernel<T, VEC, NVV, true, false><<<(unsigned)a.rows, LN_THREADS, 0, rt.stream()>>>(a);              \
             rt.post_launch("layer_norm_bwd_kernel");                                                                            \
@@ -498,7 +619,7 @@ static void ln_bwd_typed(const LnArgs &a, int ctas, bool write_dx) {
     rt.post_launch("layer_norm_bwd_kernel");
 }
 
-// dx may be null (input needs no gradient); dgain_partial is [layer_norm_bwd_ctas(rows), E] fp32
+// dx may be null (input needs no gradient); dgain_partial is [layer_norm_bwd_ctas(rows, dx != null), E] fp32
 void launch_layer_norm_bwd(const void *x, const void *gain, const void *dy, const float *mean, const float *rstd, void *dx,
                            float *dgain_partial, int ctas, int dtype, int64_t rows, int64_t E, bool rms) {
     if (rows == 0) return;

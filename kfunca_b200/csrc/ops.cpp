@@ -391,7 +391,7 @@ struct LayerNormGrad : GradFunction {
         const bool need_dx = inputs[0].requires_grad();
         Tensor dx;
         if (need_dx) dx = empty(x.sizes(), x.dtype(), x.device());
-        const int ctas = layer_norm_bwd_ctas(rows);
+        const int ctas = layer_norm_bwd_ctas(rows, need_dx);
         Tensor partial = rows > 0 ? empty({(int64_t)ctas, E}, KF_FLOAT, x.device()) : zeros({(int64_t)ctas, E}, KF_FLOAT, x.device());
         const float *st = reinterpret_cast<const float *>(stats.data());
         launch_layer_norm_bwd(x.data(), gain.data(), g.data(), st, st + rows, need_dx ? dx.data() : nullptr,
@@ -1007,6 +1007,12 @@ void gemm_host(const void *a_host, const void *b_host, void *c_host, int64_t M, 
     Tensor dB = empty({K, N}, dtype, dev);
     Tensor dA[2] = {empty({slab_rows, K}, dtype, dev), empty({slab_rows, K}, dtype, dev)};
     Tensor dC[2] = {empty({slab_rows, N}, dtype, dev), empty({slab_rows, N}, dtype, dev)};
+    // the slabs are touched by the two copy streams as well: the pool fences those streams when the slabs go back to it
+    rt.pool().record_stream(dB.data(), up);
+    for (int i = 0; i < 2; ++i) {
+        rt.pool().record_stream(dA[i].data(), up);
+        rt.pool().record_stream(dC[i].data(), down);
+    }
     // the copy streams start after everything already queued on the library stream (the pool hands out memory in its order)
     KF_CUDA(cudaEventRecord(ev_b, rt.stream()));
     KF_CUDA(cudaStreamWaitEvent(up, ev_b, 0));

@@ -366,6 +366,14 @@ PYBIND11_MODULE(_kfunca, m) {
         for (int i = 0; i < 3; ++i) st[i].assign(strides + i * KF_MAX_DIMS, strides + i * KF_MAX_DIMS + ndim);
         return py::make_tuple(sh, st, (kf_dtype_t)common);
     });
+    m.def("debug_pool_fences", [](std::vector<int> kind, std::vector<int64_t> arg, std::vector<int64_t> arg2) {
+        std::vector<int64_t> log(kind.size() * 4 + 4);
+        int n = 0;
+        ck(kf_debug_pool_fences(kind.data(), arg.data(), arg2.data(), (int)kind.size(), log.data(), (int)log.size(), &n));
+        log.resize(std::min<size_t>((size_t)n, log.size()));
+        return py::make_tuple(log, n);
+    });
+    m.def("record_stream", [](const PyTensor &t, uintptr_t stream) { ck(kf_record_stream(t.get(), reinterpret_cast<void *>(stream))); });
     m.def("debug_pool_trace", [](std::vector<int64_t> ops) {
         std::vector<int64_t> offs(ops.size());
         int64_t stats[3];

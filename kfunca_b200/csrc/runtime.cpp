@@ -47,7 +47,7 @@ void *Pool::allocate(size_t bytes) {
     const size_t size = round_size(bytes);
     const bool small = size <= kSmallLimit;
     auto &fl = small ? free_small_ : free_large_;
-    Block key{nullptr, size, true, nullptr, nullptr, nullptr, small};
+    Block key{nullptr, size, true, nullptr, nullptr, nullptr, small, {}};
     auto it = fl.lower_bound(&key);
     Block *b = nullptr;
     if (it != fl.end()) {  // best fit; the remainder is split off below and coalesces back on release
@@ -81,11 +81,11 @@ void *Pool::allocate(size_t bytes) {
         ++n_raw_;
         reserved_ += (int64_t)asz;
         arenas_[(char *)raw] = asz;
-        b = new Block{(char *)raw, asz, true, nullptr, nullptr, (char *)raw, small};
+        b = new Block{(char *)raw, asz, true, nullptr, nullptr, (char *)raw, small, {}};
     }
     const size_t rem = b->size - size;
     if (rem >= (small ? kGranule : kMinLargeSplit)) {
-        Block *r = new Block{b->ptr + size, rem, true, b, b->next, b->arena, small};
+        Block *r = new Block{b->ptr + size, rem, true, b, b->next, b->arena, small, {}};
         if (b->next) b->next->prev = r;
         b->next = r;
         b->size = size;
@@ -106,6 +106,12 @@ void Pool::release(void *ptr) {
     Block *b = it->second;
     live_.erase(it);
     in_use_ -= (int64_t)b->size;
+    // side-stream users first: after these fences the library stream's order covers every use of the block
+    for (void *st : b->streams) {
+        if (fence_) fence_(st, ctx_);
+        ++n_fence_;
+    }
+    b->streams.clear();
     b->free = true;
     auto &fl = b->small ? free_small_ : free_large_;
     if (b->prev && b->prev->free) {  // coalesce with the left neighbour
@@ -126,6 +132,17 @@ void Pool::release(void *ptr) {
         delete n;
     }
     fl.insert(b);
+}
+
+void Pool::record_stream(const void *ptr, void *stream) {
+    if (!ptr) return;
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = live_.upper_bound(const_cast<void *>(ptr));  // first block starting after ptr; the owner is the one before it
+    KF_CHECK(it != live_.begin(), "pool: record_stream on memory the pool does not own");
+    --it;
+    Block *b = it->second;
+    KF_CHECK((const char *)ptr < b->ptr + b->size, "pool: record_stream on memory the pool does not own");
+    if (std::find(b->streams.begin(), b->streams.end(), stream) == b->streams.end()) b->streams.push_back(stream);
 }
 
 void Pool::empty_cache() {
@@ -176,6 +193,10 @@ static void cuda_raw_free(void *p, void *) {
     cudaFree(p);
 }
 
+static void cuda_fence(void *stream, void *) {
+    if (g_rt) g_rt->wait_for_stream(reinterpret_cast<cudaStream_t>(stream));
+}
+
 bool Runtime::initialised() { return g_rt != nullptr; }
 
 void Runtime::select_device(int device) {
@@ -223,7 +244,23 @@ Runtime::Runtime(int device) : device_(device) {
     std::snprintf(props_.name, sizeof(props_.name), "%s", p.name);
     KF_CHECK(p.major == 10, "kfunca_b200 is built for sm_100a only; device ", device, " is sm_", p.major, p.minor);
     KF_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-    pool_.reset(new Pool(cuda_raw_alloc, cuda_raw_free, nullptr));
+    pool_.reset(new Pool(cuda_raw_alloc, cuda_raw_free, nullptr, cuda_fence));
+}
+
+void Runtime::wait_for_stream(cudaStream_t other) {
+    if (other == stream_) return;
+    std::lock_guard<std::mutex> g(fence_mu_);
+    if (fence_events_.size() < 16) {
+        cudaEvent_t ev;
+        KF_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        fence_events_.push_back(ev);
+        fence_next_ = fence_events_.size() - 1;
+    } else {
+        fence_next_ = (fence_next_ + 1) % fence_events_.size();
+    }
+    cudaEvent_t ev = fence_events_[fence_next_];
+    KF_CUDA(cudaEventRecord(ev, other));
+    KF_CUDA(cudaStreamWaitEvent(stream_, ev, 0));
 }
 
 void Runtime::h2d(void *dst, const void *src, size_t bytes, bool sync_after) {

@@ -26,8 +26,13 @@ namespace kf {
 // ------------------------------------------------------------------------------------------------
 // Stream-ordered pool.  Memory is carved out of large arenas (cudaMalloc'ed once, 2 MiB granular)
 // with best-fit + split + coalesce.  "Stream-ordered" = a freed block goes straight back to the free
-// list with NO device synchronisation: every kernel and copy of this library is issued on the one
+// list with NO device synchronisation: kernels and copies of this library are issued on the one
 // library stream, so any later user of the block is ordered after the last kernel that touched it.
+// Work on OTHER streams (the copy streams of gemm_host, the NCCL communication stream, a caller's
+// stream holding a zero-copy alias) must be announced with record_stream(ptr, stream): when such a
+// block is released, the library stream first waits for everything enqueued so far on every
+// recorded stream (event record + stream wait, no host synchronisation), so that the stream order
+// of the library stream again covers every use of the memory.
 // Host-visible reads (D2H) synchronise the stream themselves.
 // The backing allocator is pluggable so the host logic is testable without a GPU.
 // ------------------------------------------------------------------------------------------------
@@ -35,11 +40,15 @@ class Pool {
 public:
     using RawAlloc = void *(*)(size_t bytes, void *ctx);
     using RawFree = void (*)(void *ptr, void *ctx);
-    Pool(RawAlloc a, RawFree f, void *ctx) : raw_alloc_(a), raw_free_(f), ctx_(ctx) {}
+    using Fence = void (*)(void *stream, void *ctx);  // make the library stream wait for `stream`'s work enqueued so far
+    Pool(RawAlloc a, RawFree f, void *ctx, Fence fence = nullptr) : raw_alloc_(a), raw_free_(f), ctx_(ctx), fence_(fence) {}
     ~Pool();
 
     void *allocate(size_t bytes);
     void release(void *ptr);
+    // `ptr` (any address inside a live block) is in use by work enqueued on `stream`, which is not the library stream
+    void record_stream(const void *ptr, void *stream);
+    int64_t fences_issued() const { return n_fence_; }
     void empty_cache();
     std::string report() const;
 
@@ -58,6 +67,7 @@ private:
         Block *prev, *next;  // address-ordered neighbours inside the same arena
         char *arena;
         bool small;
+        std::vector<void *> streams;  // side streams that touched the block since it was allocated (record_stream)
     };
     struct Cmp {
         bool operator()(const Block *a, const Block *b) const {
@@ -70,7 +80,8 @@ private:
     RawAlloc raw_alloc_;
     RawFree raw_free_;
     void *ctx_;
-    int64_t in_use_ = 0, reserved_ = 0, n_raw_ = 0, peak_ = 0;
+    Fence fence_ = nullptr;
+    int64_t in_use_ = 0, reserved_ = 0, n_raw_ = 0, peak_ = 0, n_fence_ = 0;
     mutable std::mutex mu_;
 };
 
@@ -98,6 +109,8 @@ public:
     void d2h(void *dst, const void *src, size_t bytes, bool sync_after);
     void d2d(void *dst, const void *src, size_t bytes);
     void memset_async(void *dst, int v, size_t bytes);
+    // the library stream waits (on the device) for everything enqueued so far on `other`
+    void wait_for_stream(cudaStream_t other);
     // scratch that lives until the next call on the stream needs it: plain pool memory, freed stream-ordered
     void *scratch(size_t bytes) { return pool_->allocate(bytes); }
     void scratch_free(void *p) { pool_->release(p); }
@@ -110,6 +123,9 @@ private:
     cudaStream_t stream_ = nullptr;
     DeviceProps props_;
     std::unique_ptr<Pool> pool_;
+    std::mutex fence_mu_;
+    std::vector<cudaEvent_t> fence_events_;  // reused round-robin: a stream wait captures the record it was enqueued after
+    size_t fence_next_ = 0;
 };
 
 // RAII scratch buffer

@@ -164,6 +164,21 @@ def test_pool_allocator_reuse_split_coalesce():
     assert reserved == 2 * MiB and in_use == 1024
 
 
+def test_pool_fences_side_streams_on_release():
+    """record_stream: a block used on other streams is fenced (library stream waits for each such stream, once) when it is released;
+    blocks nobody announced are released without a fence; the record dies with the block (its next tenant starts clean)."""
+    A, F, R = 0, 1, 2
+    log, n = kf.debug_pool_fences([A, R, R, R, F], [4096, 0, 0, 0, 0], [0, 11, 22, 11, 0])
+    assert n == 2 and log == [11, 22]
+    log, n = kf.debug_pool_fences([A, A, R, F, F], [4096, 4096, 1, 0, 1], [0, 0, 7, 0, 0])
+    assert log == [7]  # only the announced block is fenced
+    # released + reallocated at the same address: the new tenant carries no stale streams
+    log, n = kf.debug_pool_fences([A, R, F, A, F], [4096, 0, 0, 4096, 3], [0, 5, 0, 0, 0])
+    assert log == [5] and n == 1
+    with pytest.raises(RuntimeError):
+        kf.debug_pool_fences([R], [0], [1])
+
+
 def test_pool_grows_in_slabs_once_it_is_large():
     """>= 1 GiB reserved: a miss reserves a quarter of the pool (not the exact request), so a repeating allocation pattern
     stops calling the driver (steady state of a training step)."""

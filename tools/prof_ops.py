@@ -1,6 +1,6 @@
 """Profiling workload: one pass over each hot-path family at its BASELINE size (for `ncu`; never a bench number).
 
-  python tools/prof_ops.py [family ...]      families: ew reduce permute topk gemm attn attn_bwd
+  python tools/prof_ops.py [family ...]      families: ew reduce permute topk gemm gemm_f32 norm attn attn_bwd
 """
 import os
 import sys
@@ -45,6 +45,28 @@ if "gemm" in fams:
     for _ in range(REPS):
         kf.gemm(A, B, 1.0, 0.0)
     del A, B
+if "gemm_f32" in fams:
+    n = 8192
+    A = kf.empty([n, n], kf.float, 0)
+    B = kf.empty([n, n], kf.float, 0)
+    A.random_uniform_(1, -1.0, 1.0)
+    B.random_uniform_(2, -1.0, 1.0)
+    for _ in range(REPS):
+        kf.gemm(A, B, 1.0, 0.0)
+    del A, B
+if "norm" in fams:
+    N = 4096
+    a = kf.from_numpy(rng.uniform(-10, 10, (N, N)).astype(np.float32), 0)
+    g = kf.from_numpy(rng.uniform(0.5, 1.5, (1, N)).astype(np.float32), 0)
+    dy = kf.from_numpy(rng.uniform(-1, 1, (N, N)).astype(np.float32), 0)
+    a.set_requires_grad(True)
+    for _ in range(REPS):
+        a.mean_var(1, False)
+        a.norm_stat(0)
+        y = kf.layer_norm(a, g, 1e-5)
+        a.zero_grad()
+        y.backward(dy)
+    del a, g, dy, y
 if fams & {"attn", "attn_bwd"}:
     Bq, H, S, D = (8, 32, 4096, 128) if "KF_PROF_SMALL" not in os.environ else (1, 4, 4096, 128)
     q = kf.empty([Bq, H, S, D], kf.bfloat16, 0)

@@ -80,6 +80,9 @@ int kf_event_elapsed_ms(kf_event_t start, kf_event_t stop, float *ms);
 int kf_event_destroy(kf_event_t ev);
 
 /* pinned host staging buffers for the H2D/D2H legs (ref: dmemcpy_h2d/d2h, src/device/memory_engine.cu:6-28) */
+/* NUMA node of the process's GPU (-1 when the platform does not say) and the kernel's cpulist string of that node ("0-31,64-95");
+ * kf_host_alloc_pinned binds itself to those CPUs while it allocates and first touches the buffer (KF_NUMA=0 disables). */
+int kf_numa_info(int *node, char *cpulist, size_t cap);
 int kf_host_alloc_pinned(size_t bytes, void **ptr);
 int kf_host_free_pinned(void *ptr);
 

@@ -1,7 +1,12 @@
 // extern "C" boundary: every entry point of include/kfunca_b200.h.  Thin by construction — argument
 // marshalling, exception -> status code + thread-local message, nothing else.
+#include <sched.h>
+
+#include <cctype>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <string>
 
 #include "ops.h"
 #include "runtime.h"
@@ -148,10 +153,80 @@ int kf_event_destroy(kf_event_t ev) {
     }
     KF_API_END
 }
+// NUMA placement of the host side of the boundary: pinned buffers are allocated (and first touched) by a thread bound to the CPUs of
+// the GPU's own NUMA node, so that at N ranks per box every rank's H2D / D2H traffic stays on the memory controller next to its PCIe
+// root instead of all ranks sharing node 0 (measured in round 1: e2e 5.9 -> 21.8 ms per step from 1 to 8 ranks).  KF_NUMA=0 disables.
+static int gpu_numa_node() {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), Runtime::get().device()) != cudaSuccess) return -1;
+    for (char *c = bus; *c; ++c) *c = (char)std::tolower(*c);
+    const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+    FILE *f = std::fopen(path.c_str(), "r");
+    if (!f) return -1;
+    int node = -1;
+    if (std::fscanf(f, "%d", &node) != 1) node = -1;
+    std::fclose(f);
+    return node;
+}
+static std::string node_cpulist(int node) {
+    if (node < 0) return "";
+    char path[96];
+    std::snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    FILE *f = std::fopen(path, "r");
+    if (!f) return "";
+    char buf[1024] = {0};
+    const bool ok = std::fgets(buf, sizeof(buf), f) != nullptr;
+    std::fclose(f);
+    std::string s = ok ? buf : "";
+    while (!s.empty() && (s.back() == '\n' || s.back() == ' ')) s.pop_back();
+    return s;
+}
+static bool parse_cpulist(const std::string &s, cpu_set_t *set) {  // "0-31,64-95"
+    CPU_ZERO(set);
+    int n = 0;
+    size_t i = 0;
+    while (i < s.size()) {
+        char *end = nullptr;
+        const long a = std::strtol(s.c_str() + i, &end, 10);
+        if (end == s.c_str() + i) return false;
+        long b = a;
+        i = (size_t)(end - s.c_str());
+        if (i < s.size() && s[i] == '-') {
+            b = std::strtol(s.c_str() + i + 1, &end, 10);
+            i = (size_t)(end - s.c_str());
+        }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) {
+            CPU_SET((int)c, set);
+            ++n;
+        }
+        if (i < s.size() && s[i] == ',') ++i;
+    }
+    return n > 0;
+}
+
+int kf_numa_info(int *node, char *cpulist, size_t cap) {
+    KF_API_BEGIN
+    const int nd = gpu_numa_node();
+    if (node) *node = nd;
+    if (cpulist && cap) std::snprintf(cpulist, cap, "%s", node_cpulist(nd).c_str());
+    KF_API_END
+}
+
 int kf_host_alloc_pinned(size_t bytes, void **ptr) {
     KF_API_BEGIN
     Runtime::get();
-    KF_CUDA(cudaMallocHost(ptr, bytes ? bytes : 1));
+    const char *env = std::getenv("KF_NUMA");
+    cpu_set_t old_set, node_set;
+    bool bound = false;
+    if (!(env && env[0] == '0') && sched_getaffinity(0, sizeof(old_set), &old_set) == 0 && parse_cpulist(node_cpulist(gpu_numa_node()), &node_set)) {
+        cpu_set_t both;
+        CPU_AND(&both, &old_set, &node_set);  // stay inside whatever cpuset the launcher gave us
+        if (CPU_COUNT(&both) > 0) bound = sched_setaffinity(0, sizeof(both), &both) == 0;
+    }
+    const cudaError_t e = cudaMallocHost(ptr, bytes ? bytes : 1);
+    if (e == cudaSuccess && bound) std::memset(*ptr, 0, bytes ? bytes : 1);  // first touch on the local node
+    if (bound) sched_setaffinity(0, sizeof(old_set), &old_set);
+    KF_CUDA(e);
     KF_API_END
 }
 int kf_host_free_pinned(void *ptr) {

@@ -18,6 +18,7 @@
 // TMEM: 512 columns = S_0 | S_1 | O_0 | O_1.  Shared memory: 2 Q tiles + 4 K/V slots (192 KB at D = 128), one CTA per SM.
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "ew_common.cuh"
 #include "tc_common.cuh"
@@ -540,6 +541,323 @@ __device__ __forceinline__ void attn_fwd_tc_body(const CUtensorMap &tmap_q, cons
     }
 }
 
+// =====================================================================================================================
+// Forward, variant "P through shared memory" (KF_ATTN_FWD=ps): the next S of a tile no longer waits for the tile's P V.
+// In the kernel above P overwrites S in tensor memory, so the chain  S(j) -> softmax(j) -> [P V(j), S(j+1)] -> softmax(j+1)
+// is serial per tile: with two tiles ping-ponging, the tensor pipe has 2048 clk of work per KV block against a per-tile cycle of
+// softmax + 1024 + two ~250 clk hand-overs (measured ~3300 clk per block).  Here the softmax warps signal "S is in registers"
+// right after their tcgen05.ld, the MMA warp issues S(j+1) at once into the same columns, and P travels through a 16 KB
+// shared-memory buffer per tile in two 64-key halves (K-major, 128B swizzle, written with st.shared.v4 + fence.proxy.async,
+// read by the P V MMAs as their A operand).  The softmax warps of a tile then run block after block without waiting for the
+// tensor pipe; the pipe's work (S of the next block, the four P V halves of this one) fills in underneath.
+// Shared memory: Q 2 x 32 KB, K/V ring 4 x 32 KB, P 2 x 16 KB = 224 KB at D = 128.  TMEM: S0 | S1 | O0 | O1 as before.
+template <int D, bool BF16, bool MASKED, int POLY>
+__device__ __forceinline__ void fwd_softmax_block_ps(const uint32_t s_addr, const uint32_t o_addr, const float sc, const int lim, const bool first,
+                                                     float &m_ref, float &l_run, uint64_t *s_free, uint64_t *p_full, uint64_t *p_free, const int j,
+                                                     const uint32_t p_row, const uint32_t rsw) {
+    uint32_t s[4][32];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tmem_ld32(s_addr + (uint32_t)(c * 32), s[c]);
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(s_free);  // S(j) is in registers: the MMA warp may overwrite it with S(j+1)
+    if (MASKED) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (c * 32 + i > lim) s[c][i] = 0xff800000u;  // -inf
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+            mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
+            mx1 = fmaxf(mx1, fmaxf(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])));
+            mx2 = fmaxf(mx2, fmaxf(__uint_as_float(s[c][i + 4]), __uint_as_float(s[c][i + 5])));
+            mx3 = fmaxf(mx3, fmaxf(__uint_as_float(s[c][i + 6]), __uint_as_float(s[c][i + 7])));
+        }
+    const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+    const float m_new = fmaxf(m_ref, mx * sc);
+    const bool grow = first ? true : (m_new - m_ref > 8.f);  // lazy reference: only moves when the row max grew by more than 2^8
+    if (!first && __any_sync(0xffffffffu, grow)) {
+        // O may only be touched once every P V of the previous blocks has completed: 2 j completions of p_free
+        mbar_wait(p_free, (uint32_t)((2 * j - 1) & 1));
+        tc_fence_after();
+        const float f = grow ? ((m_ref == -INFINITY) ? 0.f : ex2_approx(m_ref - m_new)) : 1.f;
+        l_run *= f;
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+            uint32_t orr[32];
+            tmem_ld32(o_addr + (uint32_t)(c * 32), orr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * f);
+            tmem_st32(o_addr + (uint32_t)(c * 32), orr);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+    }
+    if (grow) m_ref = m_new;
+    const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+    const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(-m_use, -m_use);
+    float2 rs2 = make_float2(0.f, 0.f), rs3 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {  // 64-key halves
+        uint32_t pk[32];
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+                float2 x = __ffma2_rn(make_float2(__uint_as_float(s[2 * h + cc][i]), __uint_as_float(s[2 * h + cc][i + 1])), sc2, nm2);
+                if (((i >> 1) & 7) < POLY) {
+                    x = ex2_poly2(x);
+                } else {
+                    x.x = ex2_approx(x.x);
+                    x.y = ex2_approx(x.y);
+                }
+                if (i & 2) rs3 = __fadd2_rn(rs3, x);
+                else rs2 = __fadd2_rn(rs2, x);
+                pk[cc * 16 + (i >> 1)] = pack16t<BF16>(x);
+            }
+        // the 16 KB buffer is free once the previous half's P V MMAs have read it: 2 j + h completions of p_free
+        const int need = 2 * j + h;
+        if (need > 0) mbar_wait(p_free, (uint32_t)((need - 1) & 1));
+#pragma unroll
+        for (int c = 0; c < 8; ++c)  // this row's 128 bytes: eight 16-byte chunks, XOR-swizzled by the row index (128B swizzle atom)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + ((((uint32_t)c) ^ rsw) << 4)), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
+                         "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
+                         : "memory");
+        fence_proxy_async();  // generic-proxy stores -> visible to the MMA's async-proxy reads
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(p_full + h);
+    }
+    l_run += (rs2.x + rs2.y) + (rs3.x + rs3.y);
+}
+
+template <int D, int POLY>
+__global__ void __launch_bounds__(FaCfg<1>::THREADS, 1)
+attn_fwd_ps_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                   const __grid_constant__ CUtensorMap tmap_v, const AttnTcParams p) {
+    constexpr int ATOMS = D / 64;
+    constexpr int TILE_BYTES = 128 * D * 2;
+    constexpr int ATOM_BYTES = 128 * 128;
+    constexpr int P_BYTES = 128 * 128;  // one 64-key half: 128 rows x 128 B
+    constexpr uint32_t TMEM_COLS = 512, O_COL = 256;
+    constexpr int NS = FA_NSTAGE;
+    constexpr int W_MMA = 8, W_TMA = 9;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char *sQ = smem;
+    unsigned char *sKV = smem + 2 * TILE_BYTES;
+    unsigned char *sP = sKV + NS * TILE_BYTES;  // [2 tiles] 16 KB
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sP + 2 * P_BYTES);
+    uint64_t *q_full = bars + 0;
+    uint64_t *kv_full = bars + 1, *kv_empty = bars + 1 + NS;
+    uint64_t *s_full = bars + 1 + 2 * NS;  // [2]
+    uint64_t *s_free = s_full + 2;         // [2]
+    uint64_t *p_full = s_free + 2;         // [2 tiles][2 halves]
+    uint64_t *p_free = p_full + 4;         // [2]: one completion per P V half
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(p_free + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bh = blockIdx.x / p.npairs;
+    const int b_idx = bh / p.H, h_idx = bh % p.H;
+    const int pr = p.npairs - 1 - (blockIdx.x % p.npairs);  // heaviest pairs first
+    const int q0 = pr * 2 * FA_BQ;
+    auto blocks_of = [&](int t) {
+        const int64_t q0t = (int64_t)q0 + t * FA_BQ;
+        const int64_t kv_end = min((int64_t)p.Skv, q0t + FA_BQ);
+        return q0t < p.Sq ? (int)((kv_end + FA_BKV - 1) / FA_BKV) : 0;
+    };
+    const int nblk0 = blocks_of(0), nblk1 = blocks_of(1);
+    const int nmax = max(nblk0, nblk1);
+
+    if (warp == W_TMA && lane == 0) {
+        prefetch_tmap(&tmap_q);
+        prefetch_tmap(&tmap_k);
+        prefetch_tmap(&tmap_v);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&kv_empty[s], 1);
+        }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(&s_full[t], 1);
+            mbar_init(&s_free[t], 4);
+            mbar_init(&p_full[2 * t], 4);
+            mbar_init(&p_full[2 * t + 1], 4);
+            mbar_init(&p_free[t], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == W_MMA) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= 8) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FaCfg<1>::REG_CTRL));
+      if (warp == W_TMA) {
+        // ===================================================== TMA producer: Q tiles once; K_0, V_0, K_1, V_1, ... through the ring
+        if (lane == 0) {
+            const int ntile_q = nblk1 > 0 ? 2 : 1;
+            mbar_arrive_expect_tx(q_full, ntile_q * TILE_BYTES);
+            for (int t = 0; t < ntile_q; ++t)
+#pragma unroll
+                for (int a = 0; a < ATOMS; ++a) tma_load_4d(sQ + t * TILE_BYTES + a * ATOM_BYTES, &tmap_q, q_full, a * 64, q0 + t * FA_BQ, h_idx, b_idx);
+            for (int i = 0; i < 2 * nmax; ++i) {
+                const int s = i % NS;
+                const int kv0 = (i >> 1) * FA_BKV;
+                const CUtensorMap *tm = (i & 1) ? &tmap_v : &tmap_k;
+                mbar_wait(&kv_empty[s], (uint32_t)(((i / NS) & 1) ^ 1));
+                mbar_arrive_expect_tx(&kv_full[s], TILE_BYTES);
+#pragma unroll
+                for (int a = 0; a < ATOMS; ++a) tma_load_4d(sKV + s * TILE_BYTES + a * ATOM_BYTES, tm, &kv_full[s], a * 64, kv0, h_idx, b_idx);
+            }
+        }
+        __syncwarp();
+      } else if (warp == W_MMA) {
+        // ===================================================== MMA issuer
+        const bool leader = elect_one();
+        {
+            const int fmt = p.is_bf16 ? 1 : 0;
+            const uint32_t idesc_s = make_idesc_f16(fmt, 0, 0, FA_BQ, FA_BKV);
+            const uint32_t idesc_pv = make_idesc_f16(fmt, 0, 1, FA_BQ, D);  // A = P K-major (smem), B = V MN-major
+            const uint32_t q_addr = smem_u32(sQ), kv_addr = smem_u32(sKV), p_addr = smem_u32(sP);
+            auto slot_of = [&](int i) {  // ring load i (K_j = 2 j, V_j = 2 j + 1): wait until it has landed, return its address
+                mbar_wait(&kv_full[i % NS], (uint32_t)((i / NS) & 1));
+                return kv_addr + (uint32_t)((i % NS) * TILE_BYTES);
+            };
+            auto issue_s = [&](int t, uint32_t k_addr) {
+#pragma unroll
+                for (int kk = 0; kk < D / 16; ++kk) {
+                    const uint32_t off = (uint32_t)((kk >> 2) * ATOM_BYTES + (kk & 3) * 32);
+                    umma_f16_p(tmem_base + (uint32_t)(t * 128), make_sw128_desc(q_addr + t * TILE_BYTES + off, 0, 1024),
+                               make_sw128_desc(k_addr + off, 0, 1024), idesc_s, kk ? 1u : 0u, leader);
+                }
+            };
+            auto issue_pv_half = [&](int t, uint32_t v_addr, bool accumulate, int half) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {  // 64 keys = 4 k-steps: A = 32 B further along the P row, B = 16 more rows of V
+                    umma_f16_p(tmem_base + O_COL + (uint32_t)(t * D), make_sw128_desc(p_addr + t * P_BYTES + kk * 32, 0, 1024),
+                               make_sw128_desc(v_addr + (half * 4 + kk) * 2048, ATOM_BYTES, 1024), idesc_pv, (accumulate || kk) ? 1u : 0u, leader);
+                }
+            };
+            mbar_wait(q_full, 0);
+            {
+                const uint32_t k0 = slot_of(0);
+                tc_fence_after();
+                if (nblk0 > 0) {
+                    issue_s(0, k0);
+                    umma_commit_p(&s_full[0], leader);
+                }
+                if (nblk1 > 0) {
+                    issue_s(1, k0);
+                    umma_commit_p(&s_full[1], leader);
+                }
+                umma_commit_p(&kv_empty[0], leader);
+            }
+            for (int j = 0; j < nmax; ++j) {
+                const uint32_t par = (uint32_t)(j & 1);
+                // ---- S of the next block for both tiles, as soon as their softmax warps hold S(j) in registers
+                if (j + 1 < nmax) {
+                    const uint32_t kn = slot_of(2 * j + 2);
+#pragma unroll
+                    for (int t = 0; t < 2; ++t)
+                        if (j + 1 < (t ? nblk1 : nblk0)) {
+                            mbar_wait(&s_free[t], par);
+                            tc_fence_after();
+                            issue_s(t, kn);
+                            umma_commit_p(&s_full[t], leader);
+                        }
+                    umma_commit_p(&kv_empty[(2 * j + 2) % NS], leader);
+                }
+                // ---- P V of this block: half 0 of both tiles, then half 1
+                const uint32_t vj = slot_of(2 * j + 1);
+#pragma unroll
+                for (int half = 0; half < 2; ++half)
+#pragma unroll
+                    for (int t = 0; t < 2; ++t)
+                        if (j < (t ? nblk1 : nblk0)) {
+                            mbar_wait(&p_full[2 * t + half], par);
+                            tc_fence_after();
+                            issue_pv_half(t, vj, j > 0 || half > 0, half);
+                            umma_commit_p(&p_free[t], leader);
+                        }
+                umma_commit_p(&kv_empty[(2 * j + 1) % NS], leader);
+            }
+        }
+        __syncwarp();
+      }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FaCfg<1>::REG_SOFTMAX));
+        // ===================================================== softmax + epilogue: thread = one query row of tile t
+        const int t = warp >> 2, q = warp & 3;
+        const int n_t = t ? nblk1 : nblk0;
+        if (n_t > 0) {
+            const int r = q * 32 + lane;
+            const int64_t q0t = (int64_t)q0 + t * FA_BQ;
+            const int64_t m_row = q0t + r;
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+            const uint32_t s_addr = lane_addr + (uint32_t)(t * 128);
+            const uint32_t o_addr = lane_addr + O_COL + (uint32_t)(t * D);
+            const uint32_t p_row = smem_u32(sP) + (uint32_t)(t * P_BYTES + r * 128);
+            const uint32_t rsw = (uint32_t)(r & 7);
+            const float sc = p.scale_log2;
+            float m_ref = -INFINITY, l_run = 0.f;
+            for (int j = 0; j < n_t; ++j) {
+                const int kv0 = j * FA_BKV;
+                mbar_wait(&s_full[t], (uint32_t)(j & 1));
+                tc_fence_after();
+                const bool masked = (kv0 + FA_BKV - 1 > q0t) || (kv0 + FA_BKV > p.Skv);
+                const int64_t lim64 = min(m_row, p.Skv - 1) - kv0;
+                const int lim = (int)max((int64_t)-1, min(lim64, (int64_t)127));
+                if (p.is_bf16) {
+                    if (masked) fwd_softmax_block_ps<D, true, true, POLY>(s_addr, o_addr, sc, lim, j == 0, m_ref, l_run, &s_free[t], &p_full[2 * t], &p_free[t], j, p_row, rsw);
+                    else fwd_softmax_block_ps<D, true, false, POLY>(s_addr, o_addr, sc, lim, j == 0, m_ref, l_run, &s_free[t], &p_full[2 * t], &p_free[t], j, p_row, rsw);
+                } else {
+                    if (masked) fwd_softmax_block_ps<D, false, true, POLY>(s_addr, o_addr, sc, lim, j == 0, m_ref, l_run, &s_free[t], &p_full[2 * t], &p_free[t], j, p_row, rsw);
+                    else fwd_softmax_block_ps<D, false, false, POLY>(s_addr, o_addr, sc, lim, j == 0, m_ref, l_run, &s_free[t], &p_full[2 * t], &p_free[t], j, p_row, rsw);
+                }
+            }
+            // ---- epilogue: every P V half has completed (2 n_t completions of p_free) -> O / l -> 16-bit -> global, row LSE
+            mbar_wait(&p_free[t], (uint32_t)((2 * n_t - 1) & 1));
+            tc_fence_after();
+            const float inv_l = 1.f / l_run;
+            const bool row_ok = m_row < p.Sq;
+            uint16_t *orow = reinterpret_cast<uint16_t *>(p.out) + (int64_t)b_idx * p.lo.sb + (int64_t)h_idx * p.lo.sh + (row_ok ? m_row : 0) * p.lo.ss;
+#pragma unroll 1
+            for (int c = 0; c < D / 32; ++c) {
+                uint32_t orr[32];
+                tmem_ld32(o_addr + (uint32_t)(c * 32), orr);
+                tmem_ld_wait();
+                if (row_ok) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(orow + c * 32);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            w[k] = pack16(__uint_as_float(orr[8 * i + 2 * k]) * inv_l, __uint_as_float(orr[8 * i + 2 * k + 1]) * inv_l, p.is_bf16);
+                        dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+            if (row_ok && p.lse) p.lse[(int64_t)bh * p.Sq + m_row] = (m_ref + log2f(l_run)) * 0.6931471805599453f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == W_MMA) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
 template <int D, int POLY>
 __global__ void __launch_bounds__(FaCfg<1>::THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -575,9 +893,11 @@ static void launch_fwd_tc(const AttnPlan &a) {
     p.scale_log2 = (float)(1.4426950408889634 / std::sqrt((double)D));
     p.npairs = (int)((a.Sq + 2 * FA_BQ - 1) / (2 * FA_BQ));
     p.is_bf16 = bf16;
-    constexpr int SMEM = (2 + FA_NSTAGE) * 128 * D * 2 + 256 + 4096 + 1024;  // tiles + barriers + max/sum exchange + alignment slack
+    // NH = 3 stands for the "P through shared memory" kernel (one thread per row): tiles + 2 x 16 KB of P + barriers + alignment slack
+    constexpr int SMEM = NH == 3 ? (2 + FA_NSTAGE) * 128 * D * 2 + 2 * 128 * 128 + 256 + 1024 : (2 + FA_NSTAGE) * 128 * D * 2 + 256 + 4096 + 1024;
     void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnTcParams);
     if constexpr (NH == 1) kern = attn_fwd_tc_kernel<D, POLY>;
+    else if constexpr (NH == 3) kern = attn_fwd_ps_kernel<D, POLY>;
     else kern = attn_fwd_tc2_kernel<D, POLY>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -586,8 +906,8 @@ static void launch_fwd_tc(const AttnPlan &a) {
     }
     const int64_t grid = a.BH * p.npairs;
     KF_CHECK(grid < (int64_t)0x7FFFFFFF);
-    kern<<<(unsigned)grid, FaCfg<NH>::THREADS, SMEM, rt.stream()>>>(tq, tk, tv, p);
-    rt.post_launch(NH == 1 ? "attn_fwd_tc_kernel" : "attn_fwd_tc2_kernel");
+    kern<<<(unsigned)grid, FaCfg<NH == 3 ? 1 : NH>::THREADS, SMEM, rt.stream()>>>(tq, tk, tv, p);
+    rt.post_launch(NH == 1 ? "attn_fwd_tc_kernel" : NH == 3 ? "attn_fwd_ps_kernel" : "attn_fwd_tc2_kernel");
 }
 
 bool launch_attention_fwd_tc(const AttnPlan &a) {
@@ -609,9 +929,12 @@ bool launch_attention_fwd_tc(const AttnPlan &a) {
     // threads per row 1.34 ms (818 TFLOP/s) — the extra named barrier, doubled polling and 96-register budget cost more than the
     // shorter dependent chains gain, so KF_ATTN_SPLIT=2 stays an opt-in experiment
     static const int nh = std::getenv("KF_ATTN_SPLIT") ? std::atoi(std::getenv("KF_ATTN_SPLIT")) : 1;
+    const char *fwd_mode = std::getenv("KF_ATTN_FWD");  // "ps": P through shared memory, next S issued early (read per call)
+    const bool ps = fwd_mode && std::strcmp(fwd_mode, "ps") == 0;
 #define KF_FWD(DD, PP)                                   \
     do {                                                 \
-        if (nh == 1) launch_fwd_tc<DD, PP, 1>(a);        \
+        if (ps) launch_fwd_tc<DD, PP, 3>(a);             \
+        else if (nh == 1) launch_fwd_tc<DD, PP, 1>(a);   \
         else launch_fwd_tc<DD, PP, 2>(a);                \
     } while (0)
     if (a.D == 64) {

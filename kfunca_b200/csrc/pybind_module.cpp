@@ -373,6 +373,12 @@ PYBIND11_MODULE(_kfunca, m) {
         log.resize(std::min<size_t>((size_t)n, log.size()));
         return py::make_tuple(log, n);
     });
+    m.def("numa_info", []() {
+        int node = -1;
+        char buf[1024] = {0};
+        ck(kf_numa_info(&node, buf, sizeof(buf)));
+        return py::make_tuple(node, std::string(buf));
+    });
     m.def("record_stream", [](const PyTensor &t, uintptr_t stream) { ck(kf_record_stream(t.get(), reinterpret_cast<void *>(stream))); });
     m.def("debug_pool_trace", [](std::vector<int64_t> ops) {
         std::vector<int64_t> offs(ops.size());

@@ -85,12 +85,38 @@ def init_from_env() -> tuple[int, int, int]:
     selects the GPU, exchanges the NCCL id and creates the communicator.  world == 1 needs no launcher and loads no NCCL."""
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     kf.set_device(local)
+    if world > 1:
+        bind_to_gpu_numa_node()
     if world > 1 and not kf.dist_info()[0]:
         addr = os.environ.get("MASTER_ADDR", "127.0.0.1")
         port = int(os.environ.get("MASTER_PORT", "29500")) + _PORT_OFFSET
         uid = exchange_id(kf.dist_unique_id() if rank == 0 else None, rank, world, addr, port)
         kf.dist_init(uid, rank, world)
     return rank, world, local
+
+
+def _parse_cpulist(s: str) -> set[int]:
+    cpus: set[int] = set()
+    for part in filter(None, s.strip().split(",")):
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node() -> int:
+    """rank -> core affinity: run this process (and the driver / NCCL proxy threads it spawns later) on the CPUs of its GPU's NUMA
+    node, intersected with the cpuset the launcher gave it.  Returns the node (-1: unknown, nothing changed).  KF_NUMA=0 disables."""
+    if os.environ.get("KF_NUMA", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return -1
+    try:
+        node, cpulist = kf.numa_info()
+        want = _parse_cpulist(cpulist) & os.sched_getaffinity(0)
+        if node >= 0 and want:
+            os.sched_setaffinity(0, want)
+            return node
+    except (OSError, ValueError, RuntimeError):
+        pass
+    return -1
 
 
 def finalize() -> None:

@@ -93,3 +93,10 @@ def test_dist_layer_is_inert_at_world_one():
 
     src = open(d.__file__).read()
     assert "import torch" not in src  # PyTorch is not a runtime dependency of the product's multi-GPU path
+
+
+def test_cpulist_parser_for_numa_binding():
+    from kfunca_b200.dist import _parse_cpulist
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert _parse_cpulist("") == set()
+    assert _parse_cpulist("5") == {5}

@@ -2,7 +2,9 @@
 set -u
 tag=$1
 mkdir -p gpurun_out
-KF_ATTN_BWD=wide timeout 300 python tools/gpu_attn.py --parity --bwd 2>&1 | grep -E "max_|attn " 
-KF_ATTN_BWD=wide KF_ATTN_TRACE=1 timeout 300 python tools/gpu_attn.py --bwd > gpurun_out/${tag}_trace.log 2>&1; grep -B2 -A5 "absolute" gpurun_out/${tag}_trace.log | head -24 | cut -c1-190
-timeout 600 python -m pytest tests/test_attention_gpu.py tests/test_baseline_shapes_gpu.py tests/test_block_gpu.py -m gpu -q -x 2>&1 | tail -3
-timeout 300 python tools/gpu_block_probe.py 2>&1 | tail -3
+for cfg in "ps 2" "ps 0" "ps 3" "ps 4" "tc 2"; do
+  set -- $cfg
+  echo "== KF_ATTN_FWD=$1 KF_ATTN_POLY=$2"
+  KF_ATTN_FWD=$1 KF_ATTN_POLY=$2 timeout 300 python tools/gpu_attn.py --parity 2>&1 | grep -E "out max|attn fwd|rror|imed out" | cut -c1-150
+done
+KF_ATTN_FWD=ps timeout 600 python -m pytest tests/test_attention_gpu.py tests/test_baseline_shapes_gpu.py -m gpu -q -x 2>&1 | tail -3

@@ -91,12 +91,22 @@ void run(const char *name, int randomize = 0, bool tma = false, int commit_each 
     if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); return; }
     unsigned long long h[148];
     cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
-    printf("%-44s reps=%d %7.1f clk per commit -> %6.1f clk per MMA (marginal, vs reps=1: see above)\n", name, REPS, (double)h[0] / groups, (double)h[0] / groups / (8 * REPS));
+    printf("%-66s %2d MMAs per commit: %7.1f clk per commit = %5.1f clk per MMA incl. the ~270 clk commit -> wake-up\n", name, 8 * REPS, (double)h[0] / groups, (double)h[0] / groups / (8 * REPS));
 }
 
 int main() {
-    run<0, false, 8>("SS N128 x64");
-    run<5, false, 8>("alternate TS(A=cols 0-63, D=256) / SS(D=cols 128-255), 8 each");
-    run<4, false, 8>("alternate TS(A=cols 0-63, D=256) / SS(D=cols 0-127 = over A), 8 each");
+    run<0, false, 1>("SS M128 N128 K16, 8 MMAs + commit + wait");
+    run<0, false, 8>("SS M128 N128 K16, 64 MMAs per commit");
+    run<1, false, 8>("SS M128 N64  K16");
+    run<2, false, 8>("TS M128 N128 K16 (A in TMEM, B MN-major)");
+    run<3, false, 8>("SS M128 N128 K16 (B MN-major)");
+    run<0, true, 8>("SS N128 + 16 warps of tcgen05.ld");
+    run<2, true, 8>("TS N128 + 16 warps of tcgen05.ld");
+    run<0, false, 8>("SS N128, random operands", 1);
+    run<0, false, 8>("SS N128, random operands + TMA 32 KB / 16 MMAs", 1, true);
+    run<0, true, 8>("SS N128, random + TMA + 16 warps tcgen05.ld", 1, true);
+    run<0, false, 8>("SS N128, commit after every 8 MMAs (nobody waits)", 0, false, 1);
+    run<5, false, 8>("alternate TS(A = cols 0-63, D = 256) / SS(D = cols 128-255)");
+    run<4, false, 8>("alternate TS(A = cols 0-63, D = 256) / SS(D = cols 0-127, over A)");
     return 0;
 }

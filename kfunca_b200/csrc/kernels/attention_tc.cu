@@ -19,6 +19,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
+#include <algorithm>
+#include <cstdio>
 
 #include "ew_common.cuh"
 #include "tc_common.cuh"
@@ -42,6 +45,7 @@ struct AttnTcParams {
     int H;             // heads per batch entry: (b, h) = (bh / H, bh % H) for the 4-D tensor maps and the output layout
     AttnLayout lo;     // layout of `out`
     int stale;         // 1: blocks after the first take their exponentials relative to the running reference (fwd_softmax_block_stale)
+    long long *trace;  // KF_ATTN_TRACE=1 (persistent kernel): clock64() stamps of CTA 0, [256 blocks][16] + [64 items][4] at 4096; else null
 };
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -106,15 +110,16 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
 // half is signalled on its own mbarrier `p_half[..]` as soon as it is stored), running
 // row sum (per half).  `lim`: columns > lim (relative to this half) are masked.  POLY: of every 8 column pairs, this many take
 // the FMA-pipe exp2.
-template <int D, bool BF16, bool MASKED, int POLY, int NH>
+template <int D, bool BF16, bool MASKED, int POLY, int NH, bool TR = false>
 __device__ __forceinline__ void fwd_softmax_block(const uint32_t s_addr, const uint32_t p_addr, const uint32_t o_addr, const float sc, const int lim,
                                                   const bool first, float &m_ref, float &l_run, float *xch_mine, const float *xch_peer,
-                                                  const int bar_id, uint64_t *p_half) {
+                                                  const int bar_id, uint64_t *p_half, long long *tr = nullptr) {
     constexpr int NC = 4 / NH;  // 32-column chunks per thread
     uint32_t s[NC][32];
 #pragma unroll
     for (int c = 0; c < NC; ++c) tmem_ld32(s_addr + (uint32_t)(c * 32), s[c]);
     tmem_ld_wait();
+    if (TR && tr) tr[0] = clock64();
     if (MASKED) {
 #pragma unroll
         for (int c = 0; c < NC; ++c)
@@ -156,6 +161,7 @@ __device__ __forceinline__ void fwd_softmax_block(const uint32_t s_addr, const u
     }
     if (grow) m_ref = m_new;
     const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+    if (TR && tr) tr[1] = clock64() + (long long)(m_use == 12345.f);  // (depends on the maximum: the stamp cannot be hoisted)
     const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(-m_use, -m_use);
     float2 rs2 = make_float2(0.f, 0.f), rs3 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -176,12 +182,14 @@ __device__ __forceinline__ void fwd_softmax_block(const uint32_t s_addr, const u
                 else rs2 = __fadd2_rn(rs2, x);
                 pk[h * 16 + (i >> 1)] = pack16t<BF16>(x);
             }
+        if (TR && tr) tr[2 + c] = clock64() + (long long)(pk[31] == 0x12345u);
         tmem_st32(p_addr + (uint32_t)(c * 16), pk);
         // hand this 64-key half of P to the MMA warp right away: the first four k-steps of P V run under the second half's exps
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(p_half + (NH == 1 ? c / 2 : 0));
+        if (TR && tr) tr[3 + c] = clock64();
     }
     l_run += (rs2.x + rs2.y) + (rs3.x + rs3.y);
 }
@@ -374,6 +382,56 @@ __device__ __forceinline__ void fwd_softmax_block_split(const uint32_t s_addr, c
     if ((threadIdx.x & 31) == 0) mbar_arrive(p_bar);
 }
 
+// Epilogue of one query tile, thread = row: O / l -> 16-bit -> a 128B-swizzled shared-memory tile -> TMA store.  A thread-per-row
+// st.global of 16 B per lane touches 32 different 128 B lines per instruction (measured 3300 - 4000 clk per 128 x 128 tile, LSU
+// bound); staged through shared memory the rows leave as full lines and the warps are free as soon as the tile is staged.
+// `stage` holds SA 64-column atoms (128 rows x 128 B each): the whole tile at once (SA = D / 64, the per-CTA kernel stages in the
+// tile's own Q buffer, dead after the tile's last S MMA) or one atom per pass (the persistent kernel's 16 KB per tile).  WAIT_PREV:
+// an earlier store may still be reading `stage`.  Rows >= Sq are clipped by the tensor map.  `o_free`: arrived on (one lane per
+// warp) once the last O columns are in registers.  The issuer thread is the tile's thread 0; bulk-group completion is per thread.
+template <int D, int SA, bool WAIT_PREV>
+__device__ __forceinline__ void fwd_store_tile(const uint32_t o_addr, const float inv_l, const bool is_bf16, unsigned char *stage,
+                                               const CUtensorMap *tmap_o, const int row0, const int h_idx, const int b_idx, const int r,
+                                               const int bar_id, uint64_t *o_free) {
+    constexpr int ATOMS = D / 64;
+    const bool issuer = r == 0;
+#pragma unroll 1
+    for (int a0 = 0; a0 < ATOMS; a0 += SA) {
+        if (WAIT_PREV || a0 > 0) {
+            if (issuer) tma_store_wait_read<0>();
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        }
+#pragma unroll 1
+        for (int c = a0 * 2; c < (a0 + SA) * 2; ++c) {
+            uint32_t orr[32];
+            tmem_ld32(o_addr + (uint32_t)(c * 32), orr);
+            tmem_ld_wait();
+            if (o_free != nullptr && c == D / 32 - 1) {  // the last O columns are in registers: the next item's first P V may overwrite them
+                tc_fence_before();
+                __syncwarp();
+                if ((threadIdx.x & 31) == 0) mbar_arrive(o_free);
+            }
+            unsigned char *dst = stage + ((c >> 1) - a0) * (128 * 128) + r * 128;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint32_t wd[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    wd[k] = pack16(__uint_as_float(orr[8 * i + 2 * k]) * inv_l, __uint_as_float(orr[8 * i + 2 * k + 1]) * inv_l, is_bf16);
+                const int chunk = (c & 1) * 4 + i;  // 16-byte chunk of the 128 B row; the 128B swizzle XORs it with the row's low 3 bits
+                *reinterpret_cast<uint4 *>(dst + ((chunk ^ (r & 7)) << 4)) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+            }
+        }
+        fence_proxy_async();  // generic-proxy stores -> visible to the bulk copy's async-proxy reads
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (issuer) {
+#pragma unroll
+            for (int a = 0; a < SA; ++a) tma_store_4d(tmap_o, stage + a * (128 * 128), (a0 + a) * 64, row0, h_idx, b_idx);
+            tma_store_commit();
+        }
+    }
+}
+
 // One CTA = two 128-row query tiles (a 256-row "pair") of one (batch, head); the two tiles ping-pong on the
 // tensor pipe: while softmax warps work on S of tile t, the MMA warp runs P V + the next Q K^T of tile 1-t.
 // Warp roles: [0, 8 NH) softmax (tile = w / (4 NH), column half = (w / 4) % NH, TMEM lane quarter = w % 4), then the MMA issuer,
@@ -390,7 +448,7 @@ struct FaCfg {
 
 template <int D, int POLY, int NH>
 __device__ __forceinline__ void attn_fwd_tc_body(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, const CUtensorMap &tmap_v,
-                                                 const AttnTcParams &p) {
+                                                 const CUtensorMap &tmap_o, const AttnTcParams &p) {
     constexpr int ATOMS = D / 64;              // 64-element (128 B) swizzle atoms along the head dimension
     constexpr int TILE_BYTES = 128 * D * 2;    // one 128 x D 16-bit tile
     constexpr int ATOM_BYTES = 128 * 128;      // 128 rows x 128 B
@@ -614,6 +672,11 @@ __device__ __forceinline__ void attn_fwd_tc_body(const CUtensorMap &tmap_q, cons
             tc_fence_after();
             const float inv_l = 1.f / l_run;
             const bool row_ok = m_row < p.Sq;
+            if constexpr (NH == 1) {  // staged in the tile's own Q buffer (every S MMA of the tile has completed), stored by TMA
+                fwd_store_tile<D, ATOMS, false>(o_addr, inv_l, p.is_bf16, sQ + t * TILE_BYTES, &tmap_o, (int)q0t, h_idx, b_idx, r, 1 + t, nullptr);
+                if (row_ok && p.lse) p.lse[(int64_t)bh * p.Sq + m_row] = (m_ref + log2f(l_run)) * 0.6931471805599453f;
+                if (r == 0) tma_store_wait_all<0>();  // the staging buffer must outlive the bulk copy's reads
+            } else {
             uint16_t *orow = reinterpret_cast<uint16_t *>(p.out) + (int64_t)b_idx * p.lo.sb + (int64_t)h_idx * p.lo.sh + (row_ok ? m_row : 0) * p.lo.ss + h * HD;
 #pragma unroll 1
             for (int c = 0; c < HD / 32; ++c) {
@@ -633,6 +696,7 @@ __device__ __forceinline__ void attn_fwd_tc_body(const CUtensorMap &tmap_q, cons
                 }
             }
             if (h == 0 && row_ok && p.lse) p.lse[(int64_t)bh * p.Sq + m_row] = (m_ref + log2f(l_run)) * 0.6931471805599453f;
+            }
         }
     }
     tc_fence_before();
@@ -742,7 +806,8 @@ __device__ __forceinline__ void fwd_softmax_block_ps(const uint32_t s_addr, cons
 template <int D, int POLY>
 __global__ void __launch_bounds__(FaCfg<1>::THREADS, 1)
 attn_fwd_ps_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                   const __grid_constant__ CUtensorMap tmap_v, const AttnTcParams p) {
+                   const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap /*tmap_o: direct stores here*/,
+                   const AttnTcParams p) {
     constexpr int ATOMS = D / 64;
     constexpr int TILE_BYTES = 128 * D * 2;
     constexpr int ATOM_BYTES = 128 * 128;
@@ -960,17 +1025,275 @@ attn_fwd_ps_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     }
 }
 
+// =====================================================================================================================
+// Forward, PERSISTENT form (KF_ATTN_FWD=pers; the default for KV lengths <= 2048): one CTA per SM walks a static list of (batch-head, query pair) work items, heaviest pairs
+// first (longest-processing-time order: all pairs of the longest KV range over every batch-head, then the next length, ...; CTA c
+// takes items c, c + grid, c + 2 grid, ... so every CTA sees the same length profile).  The roles are those of attn_fwd_tc_body
+// (NH = 1), but the K/V ring, the TMEM allocation, the tensor maps and the barrier set-up outlive a work item:
+//   * the TMA warp loads the next item's Q tiles as soon as the last S MMA of the current item has completed (q_empty) and keeps
+//     the K/V ring running across the item boundary, so a new item never waits for cold loads;
+//   * the MMA warp issues S_0, S_1 of the next item straight after the last P V of the current one: they run under the epilogue;
+//   * the softmax warps write O out, release the tile's O columns (o_free) and start on the next item's S, which is already there.
+// Barrier phases are running counters per role (a tile can be idle in an item when Sq is ragged).  "P V of the last block done"
+// has its own barrier (o_full) so that s_full never completes two phases between two looks of a waiter.
+template <int D, int POLY>
+__global__ void __launch_bounds__(FaCfg<1>::THREADS, 1)
+attn_fwd_pers_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                     const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o, const AttnTcParams p) {
+    constexpr int ATOMS = D / 64;
+    constexpr int TILE_BYTES = 128 * D * 2;
+    constexpr int ATOM_BYTES = 128 * 128;
+    constexpr uint32_t TMEM_COLS = 512, O_COL = 256;  // S0 | S1 | O0 | O1 (P_t aliases the first 64 columns of S_t)
+    constexpr int NS = FA_NSTAGE;
+    constexpr int W_MMA = 8, W_TMA = 9;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char *sQ = smem;
+    unsigned char *sKV = smem + 2 * TILE_BYTES;
+    unsigned char *sO = smem + (2 + NS) * TILE_BYTES;  // epilogue staging: one 64-column atom (128 rows x 128 B) per tile
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (2 + NS) * TILE_BYTES + 2 * ATOM_BYTES);
+    uint64_t *q_full = bars + 0, *q_empty = bars + 1;
+    uint64_t *kv_full = bars + 2, *kv_empty = bars + 2 + NS;
+    uint64_t *s_full = bars + 2 + 2 * NS;  // [2]
+    uint64_t *p_full = s_full + 2;         // [2 tiles][2 key halves]
+    uint64_t *o_full = p_full + 4;         // [2]: every P V of the item has completed
+    uint64_t *o_free = o_full + 2;         // [2]: the epilogue has read O out of tensor memory
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_free + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwork = (int)p.BH * p.npairs;
+    // work item w -> (batch-head, pair): pairs in decreasing length, every batch-head of a length before the next length
+    auto blocks_of = [&](int q0, int t) {
+        const int64_t q0t = (int64_t)q0 + t * FA_BQ;
+        const int64_t kv_end = min((int64_t)p.Skv, q0t + FA_BQ);
+        return q0t < p.Sq ? (int)((kv_end + FA_BKV - 1) / FA_BKV) : 0;
+    };
+
+    if (warp == W_TMA && lane == 0) {
+        prefetch_tmap(&tmap_q);
+        prefetch_tmap(&tmap_k);
+        prefetch_tmap(&tmap_v);
+        prefetch_tmap(&tmap_o);
+        mbar_init(q_full, 1);
+        mbar_init(q_empty, 1);
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&kv_empty[s], 1);
+        }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(&s_full[t], 1);
+            mbar_init(&p_full[2 * t], 4);
+            mbar_init(&p_full[2 * t + 1], 4);
+            mbar_init(&o_full[t], 1);
+            mbar_init(&o_free[t], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == W_MMA) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= 8) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FaCfg<1>::REG_CTRL));
+      if (warp == W_TMA) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            int s = 0, it = 0;
+            uint32_t ph = 0;
+            for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
+                const int bh = w % (int)p.BH, pr = p.npairs - 1 - w / (int)p.BH;
+                const int b_idx = bh / p.H, h_idx = bh % p.H, q0 = pr * 2 * FA_BQ;
+                const int nblk0 = blocks_of(q0, 0), nblk1 = blocks_of(q0, 1), nmax = max(nblk0, nblk1);
+                const int ntile_q = nblk1 > 0 ? 2 : 1;
+                mbar_wait(q_empty, (uint32_t)((it & 1) ^ 1));  // the previous item's last S MMA has read Q (first item: passes at once)
+                mbar_arrive_expect_tx(q_full, ntile_q * TILE_BYTES);
+                for (int t = 0; t < ntile_q; ++t)
+#pragma unroll
+                    for (int a = 0; a < ATOMS; ++a) tma_load_4d(sQ + t * TILE_BYTES + a * ATOM_BYTES, &tmap_q, q_full, a * 64, q0 + t * FA_BQ, h_idx, b_idx);
+                for (int i = 0; i < 2 * nmax; ++i) {  // K_0, V_0, K_1, V_1, ...
+                    const int kv0 = (i >> 1) * FA_BKV;
+                    const CUtensorMap *tm = (i & 1) ? &tmap_v : &tmap_k;
+                    mbar_wait(&kv_empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&kv_full[s], TILE_BYTES);
+#pragma unroll
+                    for (int a = 0; a < ATOMS; ++a) tma_load_4d(sKV + s * TILE_BYTES + a * ATOM_BYTES, tm, &kv_full[s], a * 64, kv0, h_idx, b_idx);
+                    if (++s == NS) {
+                        s = 0;
+                        ph ^= 1;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+      } else if (warp == W_MMA) {
+        // ===================================================== MMA issuer (converged warp, elected lane issues)
+        const bool leader = elect_one();
+        const int fmt = p.is_bf16 ? 1 : 0;
+        const uint32_t idesc_s = make_idesc_f16(fmt, 0, 0, FA_BQ, FA_BKV);
+        const uint32_t idesc_pv = make_idesc_f16(fmt, 0, 1, FA_BQ, D);
+        const uint32_t q_addr = smem_u32(sQ), kv_addr = smem_u32(sKV);
+        auto issue_s = [&](int t, uint32_t k_addr) {
+#pragma unroll
+            for (int kk = 0; kk < D / 16; ++kk) {
+                const uint32_t off = (uint32_t)((kk >> 2) * ATOM_BYTES + (kk & 3) * 32);
+                umma_f16_p(tmem_base + (uint32_t)(t * 128), make_sw128_desc(q_addr + t * TILE_BYTES + off, 0, 1024),
+                           make_sw128_desc(k_addr + off, 0, 1024), idesc_s, kk ? 1u : 0u, leader);
+            }
+        };
+        auto issue_pv = [&](int t, uint32_t v_addr, bool accumulate, int half) {
+#pragma unroll
+            for (int kk = half * (FA_BKV / 32); kk < (half + 1) * (FA_BKV / 32); ++kk)
+                umma_f16_ts_p(tmem_base + O_COL + (uint32_t)(t * D), tmem_base + (uint32_t)(t * 128) + (uint32_t)(kk * 8),
+                              make_sw128_desc(v_addr + kk * 2048, ATOM_BYTES, 1024), idesc_pv, (accumulate || kk) ? 1u : 0u, leader);
+        };
+        int s = 0, it = 0;
+        uint32_t ph = 0;
+        auto next_slot = [&]() {
+            mbar_wait(&kv_full[s], ph);
+            const int cur = s;
+            if (++s == NS) {
+                s = 0;
+                ph ^= 1;
+            }
+            return cur;
+        };
+        uint32_t cp0 = 0, cp1 = 0;    // blocks of tile 0 / 1 handed over so far (phase of p_full)
+        uint32_t act0 = 0, act1 = 0;  // items in which tile 0 / 1 was active so far (phase of o_free)
+        for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
+            const int pr = p.npairs - 1 - w / (int)p.BH, q0 = pr * 2 * FA_BQ;
+            const int nblk0 = blocks_of(q0, 0), nblk1 = blocks_of(q0, 1), nmax = max(nblk0, nblk1);
+            mbar_wait(q_full, (uint32_t)(it & 1));
+            {
+                const int sk = next_slot();  // K_0
+                tc_fence_after();
+#pragma unroll
+                for (int t = 0; t < 2; ++t)
+                    if ((t ? nblk1 : nblk0) > 0) {
+                        issue_s(t, kv_addr + sk * TILE_BYTES);
+                        umma_commit_p(&s_full[t], leader);
+                    }
+                umma_commit_p(&kv_empty[sk], leader);
+                if (nmax == 1) umma_commit_p(q_empty, leader);
+            }
+            for (int j = 1; j <= nmax; ++j) {
+                const bool tri = p.trace != nullptr && blockIdx.x == 0 && cp1 < 256 && leader;
+                if (tri) p.trace[cp1 * 16 + 12] = clock64();
+                const int sv = next_slot();  // V_{j-1}
+                if (tri) p.trace[cp1 * 16 + 13] = clock64();
+                const bool has_k = j < nmax;
+                const int sk = has_k ? next_slot() : 0;  // K_j
+                if (tri) p.trace[cp1 * 16 + 14] = clock64();
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int nb_t = t ? nblk1 : nblk0;
+                    if (j - 1 < nb_t) {
+                        uint32_t &cp = t ? cp1 : cp0;
+                        const uint32_t act = t ? act1 : act0;
+                        if (j == 1 && act > 0) mbar_wait(&o_free[t], (act - 1) & 1);  // the first P V overwrites O: the previous epilogue must have read it
+                        const bool tr = p.trace != nullptr && blockIdx.x == 0 && cp < 256 && leader;
+                        if (tr) p.trace[cp * 16 + 4 + t * 4] = clock64();
+                        mbar_wait(&p_full[2 * t], cp & 1);
+                        tc_fence_after();
+                        if (tr) p.trace[cp * 16 + 5 + t * 4] = clock64();
+                        issue_pv(t, kv_addr + sv * TILE_BYTES, j > 1, 0);
+                        mbar_wait(&p_full[2 * t + 1], cp & 1);
+                        tc_fence_after();
+                        if (tr) p.trace[cp * 16 + 6 + t * 4] = clock64();
+                        issue_pv(t, kv_addr + sv * TILE_BYTES, true, 1);
+                        if (j < nb_t) {
+                            issue_s(t, kv_addr + sk * TILE_BYTES);
+                            umma_commit_p(&s_full[t], leader);
+                        } else {
+                            umma_commit_p(&o_full[t], leader);
+                        }
+                        if (tr) p.trace[cp * 16 + 7 + t * 4] = clock64();
+                        ++cp;
+                    }
+                }
+                umma_commit_p(&kv_empty[sv], leader);
+                if (has_k) umma_commit_p(&kv_empty[sk], leader);
+                if (j == nmax - 1) umma_commit_p(q_empty, leader);  // the item's last S has been issued
+            }
+            if (nblk0 > 0) ++act0;
+            if (nblk1 > 0) ++act1;
+        }
+        __syncwarp();
+      }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FaCfg<1>::REG_SOFTMAX));
+        // ===================================================== softmax + epilogue: thread = one query row of tile t
+        const int t = warp >> 2, q = warp & 3;
+        const int r = q * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t s_addr = lane_addr + (uint32_t)(t * 128);
+        const uint32_t o_addr = lane_addr + O_COL + (uint32_t)(t * D);
+        const float sc = p.scale_log2;
+        uint32_t cs = 0, co = 0;  // completions of s_full[t] / o_full[t] consumed so far
+        for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+            const int bh = w % (int)p.BH, pr = p.npairs - 1 - w / (int)p.BH;
+            const int b_idx = bh / p.H, h_idx = bh % p.H, q0 = pr * 2 * FA_BQ;
+            const int n_t = blocks_of(q0, t);
+            if (n_t == 0) continue;
+            const int64_t q0t = (int64_t)q0 + t * FA_BQ;
+            const int64_t m_row = q0t + r;
+            float m_ref = -INFINITY, l_run = 0.f;
+            for (int j = 0; j < n_t; ++j) {
+                const int kv0 = j * FA_BKV;
+                mbar_wait(&s_full[t], cs & 1);
+                ++cs;
+                tc_fence_after();
+                if (p.trace != nullptr && blockIdx.x == 0 && cs <= 256 && q == 0 && lane == 0) p.trace[(cs - 1) * 16 + t * 2] = clock64();
+                const bool masked = (kv0 + FA_BKV - 1 > q0t) || (kv0 + FA_BKV > p.Skv);  // diagonal / ragged block (CTA-uniform per tile)
+                const int64_t lim64 = min(m_row, p.Skv - 1) - kv0;                       // columns i > lim are masked
+                const int lim = (int)max((int64_t)-1, min(lim64, (int64_t)127));
+                uint64_t *p_bar = &p_full[2 * t];
+                if (p.trace != nullptr) {  // traced run (bf16, unmasked arithmetic only on full blocks): stamps inside the block for CTA 0, warp 0 of the tile
+                    long long *tr = (blockIdx.x == 0 && cs <= 256 && q == 0 && lane == 0) ? p.trace + 8192 + (cs - 1) * 16 + t * 8 : nullptr;
+                    if (masked) fwd_softmax_block<D, true, true, POLY, 1, true>(s_addr, s_addr, o_addr, sc, lim, j == 0, m_ref, l_run, nullptr, nullptr, 0, p_bar, tr);
+                    else fwd_softmax_block<D, true, false, POLY, 1, true>(s_addr, s_addr, o_addr, sc, lim, j == 0, m_ref, l_run, nullptr, nullptr, 0, p_bar, tr);
+                } else if (p.is_bf16) {
+                    if (masked) fwd_softmax_block<D, true, true, POLY, 1>(s_addr, s_addr, o_addr, sc, lim, j == 0, m_ref, l_run, nullptr, nullptr, 0, p_bar);
+                    else fwd_softmax_block<D, true, false, POLY, 1>(s_addr, s_addr, o_addr, sc, lim, j == 0, m_ref, l_run, nullptr, nullptr, 0, p_bar);
+                } else {
+                    if (masked) fwd_softmax_block<D, false, true, POLY, 1>(s_addr, s_addr, o_addr, sc, lim, j == 0, m_ref, l_run, nullptr, nullptr, 0, p_bar);
+                    else fwd_softmax_block<D, false, false, POLY, 1>(s_addr, s_addr, o_addr, sc, lim, j == 0, m_ref, l_run, nullptr, nullptr, 0, p_bar);
+                }
+                if (p.trace != nullptr && blockIdx.x == 0 && cs <= 256 && q == 0 && lane == 0) p.trace[(cs - 1) * 16 + t * 2 + 1] = clock64();
+            }
+            // ---- epilogue: O / l -> 16-bit -> global, row LSE; then hand the O columns back to the MMA warp
+            mbar_wait(&o_full[t], co & 1);
+            ++co;
+            tc_fence_after();
+            if (p.trace != nullptr && blockIdx.x == 0 && co <= 64 && q == 0 && lane == 0) p.trace[4096 + (co - 1) * 4 + t * 2] = clock64();
+            const float inv_l = 1.f / l_run;
+            const bool row_ok = m_row < p.Sq;
+            fwd_store_tile<D, 1, true>(o_addr, inv_l, p.is_bf16, sO + t * ATOM_BYTES, &tmap_o, (int)q0t, h_idx, b_idx, r, 1 + t, &o_free[t]);
+            if (row_ok && p.lse) p.lse[(int64_t)bh * p.Sq + m_row] = (m_ref + log2f(l_run)) * 0.6931471805599453f;
+            if (p.trace != nullptr && blockIdx.x == 0 && co <= 64 && q == 0 && lane == 0) p.trace[4096 + (co - 1) * 4 + t * 2 + 1] = clock64();
+        }
+        if (r == 0) tma_store_wait_all<0>();  // the staging buffer must outlive the last bulk copy
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == W_MMA) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
 template <int D, int POLY>
 __global__ void __launch_bounds__(FaCfg<1>::THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                   const __grid_constant__ CUtensorMap tmap_v, const AttnTcParams p) {
-    attn_fwd_tc_body<D, POLY, 1>(tmap_q, tmap_k, tmap_v, p);
+                   const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o, const AttnTcParams p) {
+    attn_fwd_tc_body<D, POLY, 1>(tmap_q, tmap_k, tmap_v, tmap_o, p);
 }
 template <int D, int POLY>
 __global__ void __launch_bounds__(FaCfg<2>::THREADS, 1)
 attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                    const __grid_constant__ CUtensorMap tmap_v, const AttnTcParams p) {
-    attn_fwd_tc_body<D, POLY, 2>(tmap_q, tmap_k, tmap_v, p);
+                    const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o, const AttnTcParams p) {
+    attn_fwd_tc_body<D, POLY, 2>(tmap_q, tmap_k, tmap_v, tmap_o, p);
 }
 
 template <int D, int POLY, int NH>
@@ -985,7 +1308,7 @@ static void launch_fwd_tc(const AttnPlan &a) {
     auto map = [&](const void *ptr, int64_t S, const AttnLayout &l) {
         return make_tmap_4d_16bit(ptr, bf16, D, (uint64_t)S, (uint64_t)H, (uint64_t)B, (uint64_t)l.ss, (uint64_t)l.sh, (uint64_t)l.sb, 64, 128);
     };
-    const CUtensorMap tq = map(a.q, a.Sq, lq), tk = map(a.k, a.Skv, lk), tv = map(a.v, a.Skv, lv);
+    const CUtensorMap tq = map(a.q, a.Sq, lq), tk = map(a.k, a.Skv, lk), tv = map(a.v, a.Skv, lv), to = map(a.out, a.Sq, lo);
     AttnTcParams p{};
     p.H = (int)H;
     p.lo = lo;
@@ -1000,12 +1323,56 @@ static void launch_fwd_tc(const AttnPlan &a) {
         const char *st = std::getenv("KF_ATTN_STALE");
         p.stale = (st && st[0] == '1') ? 1 : 0;
     }
+    p.trace = nullptr;
+    if constexpr (NH == 4) {  // persistent kernel: one CTA per SM over the longest-first work list
+        constexpr int SMEM_P = (2 + FA_NSTAGE) * 128 * D * 2 + 2 * 128 * 128 + 256 + 1024;  // tiles + epilogue staging + barriers + alignment slack
+        static bool attr_p = false;
+        if (!attr_p) {
+            KF_CUDA(cudaFuncSetAttribute(attn_fwd_pers_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_P));
+            attr_p = true;
+        }
+        const int64_t nwork = a.BH * p.npairs;
+        KF_CHECK(nwork < (int64_t)0x7FFFFFFF);
+        static const bool want_trace = std::getenv("KF_ATTN_TRACE") != nullptr;
+        constexpr size_t TRACE_WORDS = 8192 + 4096;
+        Scratch trace_buf(want_trace ? TRACE_WORDS * 8 : 16);
+        if (want_trace) {
+            rt.memset_async(trace_buf.p, 0, TRACE_WORDS * 8);
+            p.trace = trace_buf.as<long long>();
+        }
+        const int64_t grid = std::min<int64_t>(nwork, rt.props().sm_count);
+        attn_fwd_pers_kernel<D, POLY><<<(unsigned)grid, FaCfg<1>::THREADS, SMEM_P, rt.stream()>>>(tq, tk, tv, to, p);
+        rt.post_launch("attn_fwd_pers_kernel");
+        if (want_trace) {  // bring-up aid: CTA 0's pipeline, per 128-key block (clocks)
+            rt.sync();
+            std::vector<long long> h(TRACE_WORDS);
+            KF_CUDA(cudaMemcpy(h.data(), trace_buf.p, h.size() * 8, cudaMemcpyDeviceToHost));
+            std::printf("[attn fwd trace] blk | tile0: S seen (delta to previous)  softmax | tile1: S seen (delta)  softmax | mma tile0: wait_p0 wait_p1 issue | mma tile1: wait_p0 wait_p1 issue\n");
+            for (int n = 0; n < 256 && (h[n * 16] || h[n * 16 + 2]); ++n) {
+                const long long *e = &h[n * 16], *pe = &h[(n ? n - 1 : 0) * 16];
+                std::printf("[attn fwd trace] %3d | %6lld %6lld | %6lld %6lld | %6lld %6lld %6lld | %6lld %6lld %6lld\n", n, e[0] - pe[0], e[1] - e[0], e[2] - pe[2],
+                            e[3] - e[2], e[5] - e[4], e[6] - e[5], e[7] - e[6], e[9] - e[8], e[10] - e[9], e[11] - e[10]);
+            }
+            std::printf("[attn fwd trace] blk | mma: ring wait V, ring wait K, end of previous issue -> loop top | softmax tile0: S seen->ld done, max, exps h0, st+arrive h0, exps h1, st+arrive h1 | tile1 same\n");
+            for (int n = 0; n < 256 && (h[n * 16] || h[n * 16 + 2]); ++n) {
+                const long long *e = &h[n * 16], *pe = &h[(n ? n - 1 : 0) * 16], *x = &h[8192 + n * 16];
+                std::printf("[attn fwd trace2] %3d | %6lld %6lld %6lld | %5lld %5lld %5lld %5lld %5lld %5lld | %5lld %5lld %5lld %5lld %5lld %5lld\n", n, e[13] - e[12], e[14] - e[13],
+                            e[12] - pe[11], x[0] - e[0], x[1] - x[0], x[2] - x[1], x[3] - x[2], x[4] - x[3], x[5] - x[4], x[8] - e[2], x[9] - x[8], x[10] - x[9],
+                            x[11] - x[10], x[12] - x[11], x[13] - x[12]);
+            }
+            for (int n = 0; n < 64 && (h[4096 + n * 4] || h[4096 + n * 4 + 2]); ++n)
+                std::printf("[attn fwd trace] item %2d epilogue tile0 %6lld clk, tile1 %6lld clk, tile1 start - tile0 start %6lld\n", n, h[4096 + n * 4 + 1] - h[4096 + n * 4],
+                            h[4096 + n * 4 + 3] - h[4096 + n * 4 + 2], h[4096 + n * 4 + 2] - h[4096 + n * 4]);
+        }
+        return;
+    }
     // NH = 3 stands for the "P through shared memory" kernel (one thread per row): tiles + 2 x 16 KB of P + barriers + alignment slack
     constexpr int SMEM = NH == 3 ? (2 + FA_NSTAGE) * 128 * D * 2 + 2 * 128 * 128 + 256 + 1024 : (2 + FA_NSTAGE) * 128 * D * 2 + 256 + 4096 + 1024;
-    void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnTcParams);
+    void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnTcParams);
     if constexpr (NH == 1) kern = attn_fwd_tc_kernel<D, POLY>;
     else if constexpr (NH == 3) kern = attn_fwd_ps_kernel<D, POLY>;
-    else kern = attn_fwd_tc2_kernel<D, POLY>;
+    else if constexpr (NH == 2) kern = attn_fwd_tc2_kernel<D, POLY>;
+    else kern = nullptr;
     static bool attr_done = false;
     if (!attr_done) {
         KF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -1013,7 +1380,7 @@ static void launch_fwd_tc(const AttnPlan &a) {
     }
     const int64_t grid = a.BH * p.npairs;
     KF_CHECK(grid < (int64_t)0x7FFFFFFF);
-    kern<<<(unsigned)grid, FaCfg<NH == 3 ? 1 : NH>::THREADS, SMEM, rt.stream()>>>(tq, tk, tv, p);
+    kern<<<(unsigned)grid, FaCfg<NH == 2 ? 2 : 1>::THREADS, SMEM, rt.stream()>>>(tq, tk, tv, to, p);
     rt.post_launch(NH == 1 ? "attn_fwd_tc_kernel" : NH == 3 ? "attn_fwd_ps_kernel" : "attn_fwd_tc2_kernel");
 }
 
@@ -1036,14 +1403,24 @@ bool launch_attention_fwd_tc(const AttnPlan &a) {
     // threads per row 1.34 ms (818 TFLOP/s) — the extra named barrier, doubled polling and 96-register budget cost more than the
     // shorter dependent chains gain, so KF_ATTN_SPLIT=2 stays an opt-in experiment
     static const int nh = std::getenv("KF_ATTN_SPLIT") ? std::atoi(std::getenv("KF_ATTN_SPLIT")) : 1;
-    const char *fwd_mode = std::getenv("KF_ATTN_FWD");  // "ps": P through shared memory, next S issued early (read per call)
+    // KF_ATTN_FWD (read per call): "pers" = persistent kernel (one CTA per SM over a longest-first work list), "cta" = one CTA per
+    // query pair, "ps" = P through shared memory with the next S issued early; unset = by KV length.  Measured with the two kernels
+    // alternating call by call (gpurun_out/r4b_fwd_ab.log, B H S constant, median ms): S = 1024 0.436 (pers) / 0.470 (cta), 2048
+    // 0.646 / 0.651, 4096 1.117 / 1.030, 8192 2.085 / 2.094, 16384 4.187 / 4.128.  Long runs are power-capped (the first six calls
+    // at S = 16384 take 3.46 ms = 1270 TFLOP/s, later ones 4.2 ms for either kernel), so the choice only matters for short items,
+    // where the persistent kernel's kept-alive ring, barriers and tensor-memory allocation win.
+    const char *fwd_mode = std::getenv("KF_ATTN_FWD");
     const bool ps = fwd_mode && std::strcmp(fwd_mode, "ps") == 0;
-#define KF_FWD(DD, PP)                                   \
-    do {                                                 \
-        if (ps) launch_fwd_tc<DD, PP, 3>(a);             \
-        else if (nh == 1) launch_fwd_tc<DD, PP, 1>(a);   \
-        else launch_fwd_tc<DD, PP, 2>(a);                \
+    const bool per_cta = fwd_mode ? std::strcmp(fwd_mode, "pers") != 0 : a.Skv > 2048;
+#define KF_FWD(DD, PP)                                                          \
+    do {                                                                        \
+        if (ps) launch_fwd_tc<DD, PP, 3>(a);                                    \
+        else if (nh == 1 && !per_cta && !p_stale) launch_fwd_tc<DD, PP, 4>(a);  \
+        else if (nh == 1) launch_fwd_tc<DD, PP, 1>(a);                          \
+        else launch_fwd_tc<DD, PP, 2>(a);                                       \
     } while (0)
+    const char *st_env = std::getenv("KF_ATTN_STALE");
+    const bool p_stale = st_env && st_env[0] == '1';
     if (a.D == 64) {
         if (poly <= 0) KF_FWD(64, 0);
         else KF_FWD(64, 3);

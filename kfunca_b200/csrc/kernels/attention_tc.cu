@@ -44,6 +44,7 @@ struct AttnTcParams {
     int is_bf16;
     int H;             // heads per batch entry: (b, h) = (bh / H, bh % H) for the 4-D tensor maps and the output layout
     AttnLayout lo;     // layout of `out`
+    int early_s;       // persistent kernel: 1 = tile 0's first S of the next item is issued during the item's last (tile-1-only) block
     int stale;         // 1: blocks after the first take their exponentials relative to the running reference (fwd_softmax_block_stale)
     long long *trace;  // KF_ATTN_TRACE=1 (persistent kernel): clock64() stamps of CTA 0, [256 blocks][16] + [64 items][4] at 4096; else null
 };
@@ -392,43 +393,51 @@ __device__ __forceinline__ void fwd_softmax_block_split(const uint32_t s_addr, c
 template <int D, int SA, bool WAIT_PREV>
 __device__ __forceinline__ void fwd_store_tile(const uint32_t o_addr, const float inv_l, const bool is_bf16, unsigned char *stage,
                                                const CUtensorMap *tmap_o, const int row0, const int h_idx, const int b_idx, const int r,
-                                               const int bar_id, uint64_t *o_free) {
-    constexpr int ATOMS = D / 64;
+                                               const int bar_id, uint64_t *o_free, long long *tr = nullptr) {
+    constexpr int ATOMS = D / 64, NC = D / 32;
     const bool issuer = r == 0;
-#pragma unroll 1
+    uint32_t orr[NC][32];  // the whole O row: every load is in flight before the first wait, and O is released at once
+#pragma unroll
+    for (int c = 0; c < NC; ++c) tmem_ld32(o_addr + (uint32_t)(c * 32), orr[c]);
+    tmem_ld_wait();
+    if (o_free != nullptr) {  // O is in registers: the next item's first P V may overwrite it
+        tc_fence_before();
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(o_free);
+    }
+    const float2 il2 = make_float2(inv_l, inv_l);
+#pragma unroll
     for (int a0 = 0; a0 < ATOMS; a0 += SA) {
         if (WAIT_PREV || a0 > 0) {
             if (issuer) tma_store_wait_read<0>();
             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         }
-#pragma unroll 1
+        if (tr) tr[(a0 / SA) * 4 + 0] = clock64();
+#pragma unroll
         for (int c = a0 * 2; c < (a0 + SA) * 2; ++c) {
-            uint32_t orr[32];
-            tmem_ld32(o_addr + (uint32_t)(c * 32), orr);
-            tmem_ld_wait();
-            if (o_free != nullptr && c == D / 32 - 1) {  // the last O columns are in registers: the next item's first P V may overwrite them
-                tc_fence_before();
-                __syncwarp();
-                if ((threadIdx.x & 31) == 0) mbar_arrive(o_free);
-            }
             unsigned char *dst = stage + ((c >> 1) - a0) * (128 * 128) + r * 128;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 uint32_t wd[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    wd[k] = pack16(__uint_as_float(orr[8 * i + 2 * k]) * inv_l, __uint_as_float(orr[8 * i + 2 * k + 1]) * inv_l, is_bf16);
+                for (int k = 0; k < 4; ++k) {
+                    const float2 v = __fmul2_rn(make_float2(__uint_as_float(orr[c][8 * i + 2 * k]), __uint_as_float(orr[c][8 * i + 2 * k + 1])), il2);
+                    wd[k] = is_bf16 ? pack16t<true>(v) : pack16t<false>(v);
+                }
                 const int chunk = (c & 1) * 4 + i;  // 16-byte chunk of the 128 B row; the 128B swizzle XORs it with the row's low 3 bits
                 *reinterpret_cast<uint4 *>(dst + ((chunk ^ (r & 7)) << 4)) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
             }
         }
+        if (tr) tr[(a0 / SA) * 4 + 1] = clock64();
         fence_proxy_async();  // generic-proxy stores -> visible to the bulk copy's async-proxy reads
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (tr) tr[(a0 / SA) * 4 + 2] = clock64();
         if (issuer) {
 #pragma unroll
             for (int a = 0; a < SA; ++a) tma_store_4d(tmap_o, stage + a * (128 * 128), (a0 + a) * 64, row0, h_idx, b_idx);
             tma_store_commit();
         }
+        if (tr) tr[(a0 / SA) * 4 + 3] = clock64();
     }
 }
 
@@ -1036,10 +1045,11 @@ attn_fwd_ps_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 //   * the softmax warps write O out, release the tile's O columns (o_free) and start on the next item's S, which is already there.
 // Barrier phases are running counters per role (a tile can be idle in an item when Sq is ragged).  "P V of the last block done"
 // has its own barrier (o_full) so that s_full never completes two phases between two looks of a waiter.
-template <int D, int POLY>
+template <int D, int POLY, bool TRACE>
 __global__ void __launch_bounds__(FaCfg<1>::THREADS, 1)
 attn_fwd_pers_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o, const AttnTcParams p) {
+    long long *const trace = TRACE ? p.trace : nullptr;  // the stamps exist only in the TRACE instance (registers of the control warps)
     constexpr int ATOMS = D / 64;
     constexpr int TILE_BYTES = 128 * D * 2;
     constexpr int ATOM_BYTES = 128 * 128;
@@ -1062,6 +1072,13 @@ attn_fwd_pers_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwork = (int)p.BH * p.npairs;
+    // round r of the static schedule: CTA c takes item r G + c in even rounds and r G + (G - 1 - c) in odd ones (G = grid).  The list is
+    // sorted by decreasing length, so a plain stride-G walk hands the CTAs that straddle a length step the longer item in EVERY
+    // round they straddle one (up to one longest item, 7 % of a CTA's work at S = 4096); the boustrophedon cancels it pairwise.
+    auto item_of = [&](int r) {
+        const int w = r * (int)gridDim.x + ((r & 1) ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x);
+        return w < nwork ? w : -1;
+    };
     // work item w -> (batch-head, pair): pairs in decreasing length, every batch-head of a length before the next length
     auto blocks_of = [&](int q0, int t) {
         const int64_t q0t = (int64_t)q0 + t * FA_BQ;
@@ -1096,13 +1113,13 @@ attn_fwd_pers_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp >= 8) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FaCfg<1>::REG_CTRL));
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(104)  /* the MMA warp keeps two items' loop state: 88 spills it; 128 x 104 + 256 x 200 = 384 x 168 */);
       if (warp == W_TMA) {
         // ===================================================== TMA producer
         if (lane == 0) {
             int s = 0, it = 0;
             uint32_t ph = 0;
-            for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
+            for (int w = item_of(0); w >= 0; w = item_of(++it)) {
                 const int bh = w % (int)p.BH, pr = p.npairs - 1 - w / (int)p.BH;
                 const int b_idx = bh / p.H, h_idx = bh % p.H, q0 = pr * 2 * FA_BQ;
                 const int nblk0 = blocks_of(q0, 0), nblk1 = blocks_of(q0, 1), nmax = max(nblk0, nblk1);
@@ -1161,30 +1178,45 @@ attn_fwd_pers_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         };
         uint32_t cp0 = 0, cp1 = 0;    // blocks of tile 0 / 1 handed over so far (phase of p_full)
         uint32_t act0 = 0, act1 = 0;  // items in which tile 0 / 1 was active so far (phase of o_free)
-        for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
+        int early_sk = -1;  // >= 0: S_0 of tile 0 of this item was issued during the previous item's last block, from this ring slot
+        for (int w = item_of(0); w >= 0; w = item_of(++it)) {
             const int pr = p.npairs - 1 - w / (int)p.BH, q0 = pr * 2 * FA_BQ;
             const int nblk0 = blocks_of(q0, 0), nblk1 = blocks_of(q0, 1), nmax = max(nblk0, nblk1);
-            mbar_wait(q_full, (uint32_t)(it & 1));
             {
-                const int sk = next_slot();  // K_0
+                int sk = early_sk;
+                if (sk < 0) {
+                    mbar_wait(q_full, (uint32_t)(it & 1));
+                    sk = next_slot();  // K_0
+                }
                 tc_fence_after();
 #pragma unroll
                 for (int t = 0; t < 2; ++t)
-                    if ((t ? nblk1 : nblk0) > 0) {
+                    if ((t ? nblk1 : nblk0) > 0 && !(t == 0 && early_sk >= 0)) {
                         issue_s(t, kv_addr + sk * TILE_BYTES);
                         umma_commit_p(&s_full[t], leader);
                     }
                 umma_commit_p(&kv_empty[sk], leader);
                 if (nmax == 1) umma_commit_p(q_empty, leader);
+                early_sk = -1;
             }
             for (int j = 1; j <= nmax; ++j) {
-                const bool tri = p.trace != nullptr && blockIdx.x == 0 && cp1 < 256 && leader;
-                if (tri) p.trace[cp1 * 16 + 12] = clock64();
+                const bool tri = trace != nullptr && blockIdx.x == 0 && cp1 < 256 && leader;
+                if (tri) trace[cp1 * 16 + 12] = clock64();
                 const int sv = next_slot();  // V_{j-1}
-                if (tri) p.trace[cp1 * 16 + 13] = clock64();
+                if (tri) trace[cp1 * 16 + 13] = clock64();
                 const bool has_k = j < nmax;
                 const int sk = has_k ? next_slot() : 0;  // K_j
-                if (tri) p.trace[cp1 * 16 + 14] = clock64();
+                if (tri) trace[cp1 * 16 + 14] = clock64();
+                if (p.early_s && !has_k && nblk0 < nmax && item_of(it + 1) >= 0) {
+                    // the item's last block belongs to tile 1 alone (the diagonal): tile 0 would idle through it and through tile 1's
+                    // hand-over.  Its first S of the NEXT item is issued now (Q and K_0 of that item are already on their way: q_empty
+                    // was committed with the last S of this item), so tile 0 leaves its epilogue straight into the next item.
+                    mbar_wait(q_full, (uint32_t)((it + 1) & 1));
+                    early_sk = next_slot();
+                    tc_fence_after();
+                    issue_s(0, kv_addr + early_sk * TILE_BYTES);
+                    umma_commit_p(&s_full[0], leader);
+                }
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
                     const int nb_t = t ? nblk1 : nblk0;
@@ -1192,15 +1224,15 @@ attn_fwd_pers_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                         uint32_t &cp = t ? cp1 : cp0;
                         const uint32_t act = t ? act1 : act0;
                         if (j == 1 && act > 0) mbar_wait(&o_free[t], (act - 1) & 1);  // the first P V overwrites O: the previous epilogue must have read it
-                        const bool tr = p.trace != nullptr && blockIdx.x == 0 && cp < 256 && leader;
-                        if (tr) p.trace[cp * 16 + 4 + t * 4] = clock64();
+                        const bool tr = trace != nullptr && blockIdx.x == 0 && cp < 256 && leader;
+                        if (tr) trace[cp * 16 + 4 + t * 4] = clock64();
                         mbar_wait(&p_full[2 * t], cp & 1);
                         tc_fence_after();
-                        if (tr) p.trace[cp * 16 + 5 + t * 4] = clock64();
+                        if (tr) trace[cp * 16 + 5 + t * 4] = clock64();
                         issue_pv(t, kv_addr + sv * TILE_BYTES, j > 1, 0);
                         mbar_wait(&p_full[2 * t + 1], cp & 1);
                         tc_fence_after();
-                        if (tr) p.trace[cp * 16 + 6 + t * 4] = clock64();
+                        if (tr) trace[cp * 16 + 6 + t * 4] = clock64();
                         issue_pv(t, kv_addr + sv * TILE_BYTES, true, 1);
                         if (j < nb_t) {
                             issue_s(t, kv_addr + sk * TILE_BYTES);
@@ -1208,7 +1240,7 @@ attn_fwd_pers_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                         } else {
                             umma_commit_p(&o_full[t], leader);
                         }
-                        if (tr) p.trace[cp * 16 + 7 + t * 4] = clock64();
+                        if (tr) trace[cp * 16 + 7 + t * 4] = clock64();
                         ++cp;
                     }
                 }
@@ -1222,7 +1254,7 @@ attn_fwd_pers_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         __syncwarp();
       }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FaCfg<1>::REG_SOFTMAX));
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(200));
         // ===================================================== softmax + epilogue: thread = one query row of tile t
         const int t = warp >> 2, q = warp & 3;
         const int r = q * 32 + lane;
@@ -1231,7 +1263,8 @@ attn_fwd_pers_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const uint32_t o_addr = lane_addr + O_COL + (uint32_t)(t * D);
         const float sc = p.scale_log2;
         uint32_t cs = 0, co = 0;  // completions of s_full[t] / o_full[t] consumed so far
-        for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+        int it = 0;
+        for (int w = item_of(0); w >= 0; w = item_of(++it)) {
             const int bh = w % (int)p.BH, pr = p.npairs - 1 - w / (int)p.BH;
             const int b_idx = bh / p.H, h_idx = bh % p.H, q0 = pr * 2 * FA_BQ;
             const int n_t = blocks_of(q0, t);
@@ -1244,13 +1277,13 @@ attn_fwd_pers_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 mbar_wait(&s_full[t], cs & 1);
                 ++cs;
                 tc_fence_after();
-                if (p.trace != nullptr && blockIdx.x == 0 && cs <= 256 && q == 0 && lane == 0) p.trace[(cs - 1) * 16 + t * 2] = clock64();
+                if (trace != nullptr && blockIdx.x == 0 && cs <= 256 && q == 0 && lane == 0) trace[(cs - 1) * 16 + t * 2] = clock64();
                 const bool masked = (kv0 + FA_BKV - 1 > q0t) || (kv0 + FA_BKV > p.Skv);  // diagonal / ragged block (CTA-uniform per tile)
                 const int64_t lim64 = min(m_row, p.Skv - 1) - kv0;                       // columns i > lim are masked
                 const int lim = (int)max((int64_t)-1, min(lim64, (int64_t)127));
                 uint64_t *p_bar = &p_full[2 * t];
-                if (p.trace != nullptr) {  // traced run (bf16, unmasked arithmetic only on full blocks): stamps inside the block for CTA 0, warp 0 of the tile
-                    long long *tr = (blockIdx.x == 0 && cs <= 256 && q == 0 && lane == 0) ? p.trace + 8192 + (cs - 1) * 16 + t * 8 : nullptr;
+                if (trace != nullptr) {  // traced run (bf16, unmasked arithmetic only on full blocks): stamps inside the block for CTA 0, warp 0 of the tile
+                    long long *tr = (blockIdx.x == 0 && cs <= 256 && q == 0 && lane == 0) ? trace + 8192 + (cs - 1) * 16 + t * 8 : nullptr;
                     if (masked) fwd_softmax_block<D, true, true, POLY, 1, true>(s_addr, s_addr, o_addr, sc, lim, j == 0, m_ref, l_run, nullptr, nullptr, 0, p_bar, tr);
                     else fwd_softmax_block<D, true, false, POLY, 1, true>(s_addr, s_addr, o_addr, sc, lim, j == 0, m_ref, l_run, nullptr, nullptr, 0, p_bar, tr);
                 } else if (p.is_bf16) {
@@ -1260,18 +1293,19 @@ attn_fwd_pers_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     if (masked) fwd_softmax_block<D, false, true, POLY, 1>(s_addr, s_addr, o_addr, sc, lim, j == 0, m_ref, l_run, nullptr, nullptr, 0, p_bar);
                     else fwd_softmax_block<D, false, false, POLY, 1>(s_addr, s_addr, o_addr, sc, lim, j == 0, m_ref, l_run, nullptr, nullptr, 0, p_bar);
                 }
-                if (p.trace != nullptr && blockIdx.x == 0 && cs <= 256 && q == 0 && lane == 0) p.trace[(cs - 1) * 16 + t * 2 + 1] = clock64();
+                if (trace != nullptr && blockIdx.x == 0 && cs <= 256 && q == 0 && lane == 0) trace[(cs - 1) * 16 + t * 2 + 1] = clock64();
             }
             // ---- epilogue: O / l -> 16-bit -> global, row LSE; then hand the O columns back to the MMA warp
             mbar_wait(&o_full[t], co & 1);
             ++co;
             tc_fence_after();
-            if (p.trace != nullptr && blockIdx.x == 0 && co <= 64 && q == 0 && lane == 0) p.trace[4096 + (co - 1) * 4 + t * 2] = clock64();
+            if (trace != nullptr && blockIdx.x == 0 && co <= 64 && q == 0 && lane == 0) trace[4096 + (co - 1) * 4 + t * 2] = clock64();
             const float inv_l = 1.f / l_run;
             const bool row_ok = m_row < p.Sq;
-            fwd_store_tile<D, 1, true>(o_addr, inv_l, p.is_bf16, sO + t * ATOM_BYTES, &tmap_o, (int)q0t, h_idx, b_idx, r, 1 + t, &o_free[t]);
+            fwd_store_tile<D, 1, true>(o_addr, inv_l, p.is_bf16, sO + t * ATOM_BYTES, &tmap_o, (int)q0t, h_idx, b_idx, r, 1 + t, &o_free[t],
+                                       (trace != nullptr && blockIdx.x == 0 && co <= 64 && r == 0) ? trace + 6144 + (co - 1) * 16 + t * 8 : nullptr);
             if (row_ok && p.lse) p.lse[(int64_t)bh * p.Sq + m_row] = (m_ref + log2f(l_run)) * 0.6931471805599453f;
-            if (p.trace != nullptr && blockIdx.x == 0 && co <= 64 && q == 0 && lane == 0) p.trace[4096 + (co - 1) * 4 + t * 2 + 1] = clock64();
+            if (trace != nullptr && blockIdx.x == 0 && co <= 64 && q == 0 && lane == 0) trace[4096 + (co - 1) * 4 + t * 2 + 1] = clock64();
         }
         if (r == 0) tma_store_wait_all<0>();  // the staging buffer must outlive the last bulk copy
     }
@@ -1324,16 +1358,22 @@ static void launch_fwd_tc(const AttnPlan &a) {
         p.stale = (st && st[0] == '1') ? 1 : 0;
     }
     p.trace = nullptr;
+    {
+        const char *es = std::getenv("KF_ATTN_EARLY");  // read per call (A/B runs)
+        p.early_s = (es && es[0] == '1') ? 1 : 0;  // measured: no gain (the next Q arrives too late for the issuer not to stall), off by default
+    }
     if constexpr (NH == 4) {  // persistent kernel: one CTA per SM over the longest-first work list
         constexpr int SMEM_P = (2 + FA_NSTAGE) * 128 * D * 2 + 2 * 128 * 128 + 256 + 1024;  // tiles + epilogue staging + barriers + alignment slack
         static bool attr_p = false;
         if (!attr_p) {
-            KF_CUDA(cudaFuncSetAttribute(attn_fwd_pers_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_P));
+            KF_CUDA(cudaFuncSetAttribute(attn_fwd_pers_kernel<D, POLY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_P));
+            if constexpr (D == 128 && POLY == 2)
+                KF_CUDA(cudaFuncSetAttribute(attn_fwd_pers_kernel<D, POLY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_P));
             attr_p = true;
         }
         const int64_t nwork = a.BH * p.npairs;
         KF_CHECK(nwork < (int64_t)0x7FFFFFFF);
-        static const bool want_trace = std::getenv("KF_ATTN_TRACE") != nullptr;
+        static const bool want_trace = std::getenv("KF_ATTN_TRACE") != nullptr && D == 128 && POLY == 2;  // the one traced instance
         constexpr size_t TRACE_WORDS = 8192 + 4096;
         Scratch trace_buf(want_trace ? TRACE_WORDS * 8 : 16);
         if (want_trace) {
@@ -1341,7 +1381,12 @@ static void launch_fwd_tc(const AttnPlan &a) {
             p.trace = trace_buf.as<long long>();
         }
         const int64_t grid = std::min<int64_t>(nwork, rt.props().sm_count);
-        attn_fwd_pers_kernel<D, POLY><<<(unsigned)grid, FaCfg<1>::THREADS, SMEM_P, rt.stream()>>>(tq, tk, tv, to, p);
+        if constexpr (D == 128 && POLY == 2) {
+            if (want_trace) attn_fwd_pers_kernel<D, POLY, true><<<(unsigned)grid, FaCfg<1>::THREADS, SMEM_P, rt.stream()>>>(tq, tk, tv, to, p);
+            else attn_fwd_pers_kernel<D, POLY, false><<<(unsigned)grid, FaCfg<1>::THREADS, SMEM_P, rt.stream()>>>(tq, tk, tv, to, p);
+        } else {
+            attn_fwd_pers_kernel<D, POLY, false><<<(unsigned)grid, FaCfg<1>::THREADS, SMEM_P, rt.stream()>>>(tq, tk, tv, to, p);
+        }
         rt.post_launch("attn_fwd_pers_kernel");
         if (want_trace) {  // bring-up aid: CTA 0's pipeline, per 128-key block (clocks)
             rt.sync();
@@ -1360,9 +1405,16 @@ static void launch_fwd_tc(const AttnPlan &a) {
                             e[12] - pe[11], x[0] - e[0], x[1] - x[0], x[2] - x[1], x[3] - x[2], x[4] - x[3], x[5] - x[4], x[8] - e[2], x[9] - x[8], x[10] - x[9],
                             x[11] - x[10], x[12] - x[11], x[13] - x[12]);
             }
-            for (int n = 0; n < 64 && (h[4096 + n * 4] || h[4096 + n * 4 + 2]); ++n)
-                std::printf("[attn fwd trace] item %2d epilogue tile0 %6lld clk, tile1 %6lld clk, tile1 start - tile0 start %6lld\n", n, h[4096 + n * 4 + 1] - h[4096 + n * 4],
+            for (int n = 0; n < 64 && (h[4096 + n * 4] || h[4096 + n * 4 + 2]); ++n) {
+                std::printf("[attn fwd trace] item %2d epilogue tile0 %6lld clk, tile1 %6lld clk, tile1 start - tile0 start %6lld |", n, h[4096 + n * 4 + 1] - h[4096 + n * 4],
                             h[4096 + n * 4 + 3] - h[4096 + n * 4 + 2], h[4096 + n * 4 + 2] - h[4096 + n * 4]);
+                for (int t = 0; t < 2; ++t) {  // per pass: wait for the staging buffer, O -> shared memory, fence + barrier, store issue
+                    const long long *e = &h[6144 + n * 16 + t * 8], st = h[4096 + n * 4 + t * 2];
+                    std::printf(" t%d: %5lld %5lld %5lld %5lld | %5lld %5lld %5lld %5lld ;", t, e[0] - st, e[1] - e[0], e[2] - e[1], e[3] - e[2], e[4] - e[3], e[5] - e[4],
+                                e[6] - e[5], e[7] - e[6]);
+                }
+                std::printf("\n");
+            }
         }
         return;
     }

@@ -67,11 +67,12 @@ for S in () if TRACE_ONLY else (1024, 2048, 4096, 8192, 16384):
     fl = 4 * B * H * S * S * D / 2
     # the two kernels alternate call by call (the GPU is power-capped: clocks drift by 10 - 20 % over tens of milliseconds, so
     # back-to-back windows of one variant each are not comparable); per variant: minimum and median over the calls
-    times = {"pers": [], "cta": []}
+    times = {"pers": [], "pers-early": [], "cta": []}
     evs = [Event() for _ in range(3)]
     for rep in range(24):
-        for mode in ("pers", "cta"):
-            os.environ["KF_ATTN_FWD"] = mode
+        for mode in times:
+            os.environ["KF_ATTN_FWD"] = mode.split("-")[0]
+            os.environ["KF_ATTN_EARLY"] = "1" if mode.endswith("early") else "0"
             if rep < 2:
                 kf.causal_attention_fwd(Q, K, V)
                 continue

@@ -473,6 +473,21 @@ def per_config(kf, Event, peaks, ref_cfg):
         e1.synchronize()
         return e0.elapsed_ms(e1) / iters
 
+    def t_calls(fn, iters=20, warm=3):
+        """SURVEY 8d protocol for the millisecond-scale kernels: >= 20 timed calls issued back to back with an event between each
+        (one synchronise at the end), median and minimum over the calls.  The GPU is power-capped: the first ~20 ms of a burst run
+        at a higher clock than what follows, so the median of a long series sits below a short burst's average."""
+        for i in range(warm):
+            fn(i % nsets)
+        ev = [Event() for _ in range(iters + 1)]
+        ev[0].record()
+        for i in range(iters):
+            fn(i % nsets)
+            ev[i + 1].record()
+        ev[-1].synchronize()
+        ms = sorted(ev[i].elapsed_ms(ev[i + 1]) for i in range(iters))
+        return ms[len(ms) // 2], ms[0]
+
     def ref_of(name):
         r = ref_cfg.get(name)
         if r is None:
@@ -488,9 +503,11 @@ def per_config(kf, Event, peaks, ref_cfg):
 
     def tensor(name, ms, flop, kernel, extra=None):
         tf = flop / ms / 1e9
+        roof = {"bound": "tensor", "frac": round(tf / tp, 4), "peak": tp, "algorithmic_flop": flop}
+        if extra and extra.get("ms_min"):  # the fastest of the calls (the un-throttled clock) next to the median the fraction is quoted on
+            roof["frac_at_min"] = round(flop / extra["ms_min"] / 1e9 / tp, 4)
         cfgs.append({"name": name, "ours": dict({"ms": round(ms, 4), "TFLOP/s": round(tf, 1), "kernel": kernel}, **(extra or {})),
-                     "roofline": {"bound": "tensor", "frac": round(tf / tp, 4), "peak": tp, "algorithmic_flop": flop},
-                     "reference": ref_of(name), "numpy": npb.get(name)})
+                     "roofline": roof, "reference": ref_of(name), "numpy": npb.get(name)})
 
     nb = N * N * 4
     mem("c1_add_fp32_4096", lambda i: A[i] + B[i], 3 * nb, "ew_pack_kernel")
@@ -530,19 +547,19 @@ def per_config(kf, Event, peaks, ref_cfg):
     rows, cols, k = C4["rows"], C4["cols"], C4["k"]
     X = kf.empty([rows, cols], kf.float, 0)
     X.random_uniform_(C4["seed"], -1e5, 1e5)
-    mem("c4_topk64_65536x32768", lambda i: X.topk(k, 1, True), rows * cols * 4 + rows * k * 12, "topk_twopass_kernel", iters=3, warm=2)
+    mem("c4_topk64_65536x32768", lambda i: X.topk(k, 1, True), rows * cols * 4 + rows * k * 12, "topk_twopass_kernel", iters=20, warm=3)
     del X
     # C2 in fp32: the dtype the reference's GEMM actually runs (gemm_kernel.cu:26-36) — ours is the tcgen05 split-precision kernel
     n = N_GEMM
     Af, Bf = kf.empty([n, n], kf.float, 0), kf.empty([n, n], kf.float, 0)
     Af.random_uniform_(1, -1.0, 1.0)
     Bf.random_uniform_(2, -1.0, 1.0)
-    ms32 = t(lambda i: kf.gemm(Af, Bf, 1.0, 0.0), iters=10, warm=3)
+    ms32, ms32_min = t_calls(lambda i: kf.gemm(Af, Bf, 1.0, 0.0))
     os.environ["KF_GEMM_F32"] = "simt"
     ms32_simt = t(lambda i: kf.gemm(Af, Bf, 1.0, 0.0), iters=3, warm=1)
     del os.environ["KF_GEMM_F32"]
     tensor("c2_gemm_fp32_8192", ms32, 2.0 * n ** 3, "split_f32_kernel x2 + gemm_f32x_kernel<6 products> (tcgen05, fp32 via 3 bf16 planes)",
-           {"ours_simt_ms": round(ms32_simt, 3), "hardware_TFLOP/s_bf16": round(6 * 2.0 * n ** 3 / ms32 / 1e9, 1)})
+           {"ms_min": round(ms32_min, 4), "ours_simt_ms": round(ms32_simt, 3), "hardware_TFLOP/s_bf16": round(6 * 2.0 * n ** 3 / ms32 / 1e9, 1)})
     cfgs[-1]["roofline"]["note"] = "frac = fp32 FLOP rate / bf16 dense peak; the kernel issues 6 bf16 MMAs per fp32 MMA, so 1/6 = 0.167 is its ceiling"
     del Af, Bf
     # C3 causal attention fwd / bwd bf16 B=8 H=32 S=4096 D=128, seeded U(-1,1) on the device
@@ -555,13 +572,14 @@ def per_config(kf, Event, peaks, ref_cfg):
 
     q, kk, v, do = (rnd(10 + i, kf.bfloat16) for i in range(4))
     fl = 4.0 * Bq * H * S * S * D / 2
-    ms_f = t(lambda i: kf.causal_attention(q, kk, v), iters=8, warm=3)
+    ms_f, ms_f_min = t_calls(lambda i: kf.causal_attention(q, kk, v))
     o, lse = kf.causal_attention_fwd(q, kk, v)
-    ms_b = t(lambda i: kf.causal_attention_bwd(do, q, kk, v, o, lse), iters=8, warm=3)
-    tensor("c3_attention_fwd_bf16", ms_f, fl, "attn_fwd_tc_kernel<128>")
+    ms_b, ms_b_min = t_calls(lambda i: kf.causal_attention_bwd(do, q, kk, v, o, lse))
+    tmin = lambda ms: {"ms_min": round(ms, 4), "TFLOP/s_at_min": None, "calls": 20, "ms_is": "median of 20 back-to-back calls"}
+    tensor("c3_attention_fwd_bf16", ms_f, fl, "attn_fwd_tc_kernel<128>", dict(tmin(ms_f_min), **{"TFLOP/s_at_min": round(fl / ms_f_min / 1e9, 1)}))
     cfgs[-1]["numpy"] = npb.get("c3_attention_fwd")
     cfgs[-1]["reference"] = {"note": "the reference has no 16-bit attention (causal_attention_kernel.cu:25); its fp32 forward is under c3_attention_fwd_fp32"}
-    tensor("c3_attention_bwd_bf16", ms_b, 2.5 * fl, "attention backward (tcgen05)")
+    tensor("c3_attention_bwd_bf16", ms_b, 2.5 * fl, "attention backward (tcgen05)", dict(tmin(ms_b_min), **{"TFLOP/s_at_min": round(2.5 * fl / ms_b_min / 1e9, 1)}))
     cfgs[-1]["reference"] = {"note": "the reference has no attention backward (SURVEY F3)"}
     tensor("c3_attention_fwd_bwd_bf16", ms_f + ms_b, 3.5 * fl, "forward + backward")
     cfgs[-1]["reference"] = {"note": "n/a (no backward in the reference)"}

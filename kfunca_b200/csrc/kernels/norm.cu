@@ -20,6 +20,7 @@
 #include <cstring>
 
 #include "ew_common.cuh"
+#include "tc_common.cuh"
 
 namespace kf {
 namespace cg = cooperative_groups;
@@ -244,9 +245,10 @@ __global__ void __launch_bounds__(LN_THREADS) layer_norm_bwd_kernel(const LnArgs
 // (raw, in registers) while the current row goes through its one barrier and its store — the load -> barrier -> store serialisation
 // that made the first one-kernel version slow (303 us at [32768, 4096] bf16) is gone.  Against the two-launch form this saves the
 // second read of x and dy (2/5 of the bytes).
-template <typename T, int VEC, int NV>
-__global__ void __launch_bounds__(LN_THREADS, 2) layer_norm_bwd_fused_kernel(const LnArgs a) {
-    __shared__ float red[2][8];
+template <typename T, int VEC, int NV, int TH>
+__global__ void __launch_bounds__(TH, 2) layer_norm_bwd_fused_kernel(const LnArgs a) {
+    constexpr int NW = TH / 32;
+    __shared__ float red[2][2 * NW];
     const int nvec = (int)(a.E / VEC);
     const T *__restrict__ gp = reinterpret_cast<const T *>(a.gain);
     float dgain[NV][VEC];
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(LN_THREADS, 2) layer_norm_bwd_fused_kernel(con
         const T *__restrict__ dy = reinterpret_cast<const T *>(a.dy) + row * a.E;
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-            const int iv = threadIdx.x + k * LN_THREADS;
+            const int iv = threadIdx.x + k * TH;
             if (iv < nvec) {
                 xo[k] = ln_ld<T, VEC>(x + (int64_t)iv * VEC);
                 dO[k] = ln_ld<T, VEC>(dy + (int64_t)iv * VEC);
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__(LN_THREADS, 2) layer_norm_bwd_fused_kernel(con
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-            const int iv = threadIdx.x + k * LN_THREADS;
+            const int iv = threadIdx.x + k * TH;
             if (iv < nvec) {
                 const Pack<T, VEC> gk = ln_ld<T, VEC>(gp + (int64_t)iv * VEC);  // 16 KB at most, L1-resident after the first row
 #pragma unroll
@@ -302,15 +304,21 @@ __global__ void __launch_bounds__(LN_THREADS, 2) layer_norm_bwd_fused_kernel(con
         s2 = ln_warp_sum(s2);
         if ((threadIdx.x & 31) == 0) {
             slot[threadIdx.x >> 5] = s1;
-            slot[4 + (threadIdx.x >> 5)] = s2;
+            slot[NW + (threadIdx.x >> 5)] = s2;
         }
         __syncthreads();
-        const float c1 = a.rms ? 0.f : ((slot[0] + slot[1]) + (slot[2] + slot[3])) / (float)a.E;
-        const float c2 = ((slot[4] + slot[5]) + (slot[6] + slot[7])) / (float)a.E;
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; w += 4) {  // fixed order: deterministic
+            t1 += (slot[w] + slot[w + 1]) + (slot[w + 2] + slot[w + 3]);
+            t2 += (slot[NW + w] + slot[NW + w + 1]) + (slot[NW + w + 2] + slot[NW + w + 3]);
+        }
+        const float c1 = a.rms ? 0.f : t1 / (float)a.E;
+        const float c2 = t2 / (float)a.E;
         T *__restrict__ dx = reinterpret_cast<T *>(a.dx) + row * a.E;
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-            const int iv = threadIdx.x + k * LN_THREADS;
+            const int iv = threadIdx.x + k * TH;
             if (iv < nvec) {
                 const Pack<T, VEC> gk = ln_ld<T, VEC>(gp + (int64_t)iv * VEC);
                 Pack<T, VEC> out;
@@ -334,10 +342,143 @@ __global__ void __launch_bounds__(LN_THREADS, 2) layer_norm_bwd_fused_kernel(con
     float *__restrict__ part = a.dgain_partial + (int64_t)blockIdx.x * a.E;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-        const int iv = threadIdx.x + k * LN_THREADS;
+        const int iv = threadIdx.x + k * TH;
         if (iv < nvec) {
 #pragma unroll
             for (int i = 0; i < VEC; ++i) part[(int64_t)iv * VEC + i] = dgain[k][i];
+        }
+    }
+}
+
+// One-pass backward, rows streamed through a shared-memory ring by bulk copies (the default).  The register-prefetch kernel above keeps
+// ONE row per CTA in flight (two CTAs per SM: 32 KB per SM for bf16 rows of 4096 — 0.50 of the HBM peak at [32768, 4096]); here an
+// elected thread keeps RING_STAGES rows of x and dy per CTA on their way with cp.async.bulk (one mbarrier per stage, complete_tx),
+// 96 KB per CTA and two CTAs per SM whatever the dtype, and the 256 threads only ever touch shared memory and registers:
+//   wait full[stage] -> x, dy of the row into registers (converted once) -> row sums (shuffle + one __syncthreads) -> the stage is
+//   free: thread 0 re-arms it with the row RING_STAGES ahead -> dx from the registers, 16-byte coalesced stores.
+// The gain and the gain-gradient sums of a thread's columns live in registers for the whole kernel.
+template <typename T, int VEC, int NV>
+__global__ void __launch_bounds__(256, 2) layer_norm_bwd_ring_kernel(const LnArgs a, const int stages) {
+    constexpr int TH = 256, NW = TH / 32;
+    extern __shared__ __align__(128) unsigned char ring_raw[];
+    __shared__ float red[2][2 * NW];
+    __shared__ uint64_t full[8];
+    const int64_t row_bytes = a.E * (int64_t)sizeof(T);
+    const int nvec = (int)(a.E / VEC);
+    auto stage_x = [&](int st) { return reinterpret_cast<const T *>(ring_raw + (int64_t)st * 2 * row_bytes); };
+    auto stage_dy = [&](int st) { return reinterpret_cast<const T *>(ring_raw + (int64_t)st * 2 * row_bytes + row_bytes); };
+    auto arm = [&](int st, int64_t row) {  // thread 0 only
+        tc::mbar_arrive_expect_tx(&full[st], (uint32_t)(2 * row_bytes));
+        const uint32_t bar = tc::smem_u32(&full[st]);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(tc::smem_u32(stage_x(st))), "l"(reinterpret_cast<uint64_t>(reinterpret_cast<const T *>(a.x) + row * a.E)), "r"((uint32_t)row_bytes), "r"(bar)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(tc::smem_u32(stage_dy(st))), "l"(reinterpret_cast<uint64_t>(reinterpret_cast<const T *>(a.dy) + row * a.E)), "r"((uint32_t)row_bytes), "r"(bar)
+                     : "memory");
+    };
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < stages; ++st) tc::mbar_init(&full[st], 1);
+        tc::fence_barrier_init();
+        for (int st = 0; st < stages; ++st) {
+            const int64_t row = (int64_t)blockIdx.x + (int64_t)st * gridDim.x;
+            if (row < a.rows) arm(st, row);
+        }
+    }
+    float gain[NV][VEC], dgain[NV][VEC];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int iv = threadIdx.x + k * TH;
+        Pack<T, VEC> gk{};
+        if (iv < nvec) gk = ln_ld<T, VEC>(reinterpret_cast<const T *>(a.gain) + (int64_t)iv * VEC);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            gain[k][i] = iv < nvec ? cvt_in<float>(gk.v[i]) : 0.f;
+            dgain[k][i] = 0.f;
+        }
+    }
+    __syncthreads();  // barrier inits visible before the first wait
+    int64_t row = blockIdx.x;
+    float mean = 0.f, rstd = 0.f;
+    if (row < a.rows) {
+        mean = a.mean[row];
+        rstd = a.rstd[row];
+    }
+    int st = 0;
+    uint32_t ph = 0;
+    for (int it = 0; row < a.rows; row += gridDim.x, ++it) {
+        const int64_t next = row + gridDim.x;
+        float mean_n = 0.f, rstd_n = 0.f;
+        if (next < a.rows) {  // the next row's statistics travel under this row's arithmetic
+            mean_n = a.mean[next];
+            rstd_n = a.rstd[next];
+        }
+        tc::mbar_wait(&full[st], ph);
+        const T *sx = stage_x(st), *sdy = stage_dy(st);
+        float xh[NV][VEC], gg[NV][VEC];  // x-hat and dy * gain of this thread's columns
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int iv = threadIdx.x + k * TH;
+            if (iv < nvec) {
+                const Pack<T, VEC> xk = ln_ld<T, VEC>(sx + (int64_t)iv * VEC), dk = ln_ld<T, VEC>(sdy + (int64_t)iv * VEC);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const float g = cvt_in<float>(dk.v[i]);
+                    xh[k][i] = (cvt_in<float>(xk.v[i]) - mean) * rstd;
+                    gg[k][i] = g * gain[k][i];
+                    dgain[k][i] = fmaf(g, xh[k][i], dgain[k][i]);
+                    s1 += gg[k][i];
+                    s2 = fmaf(gg[k][i], xh[k][i], s2);
+                }
+            }
+        }
+        float *slot = red[it & 1];
+        s1 = ln_warp_sum(s1);
+        s2 = ln_warp_sum(s2);
+        if ((threadIdx.x & 31) == 0) {
+            slot[threadIdx.x >> 5] = s1;
+            slot[NW + (threadIdx.x >> 5)] = s2;
+        }
+        __syncthreads();  // every thread has read its part of the stage: it can be refilled
+        if (threadIdx.x == 0) {
+            const int64_t refill = row + (int64_t)stages * gridDim.x;
+            if (refill < a.rows) arm(st, refill);
+        }
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; w += 4) {  // fixed order: deterministic
+            t1 += (slot[w] + slot[w + 1]) + (slot[w + 2] + slot[w + 3]);
+            t2 += (slot[NW + w] + slot[NW + w + 1]) + (slot[NW + w + 2] + slot[NW + w + 3]);
+        }
+        const float c1 = a.rms ? 0.f : t1 / (float)a.E;
+        const float c2 = t2 / (float)a.E;
+        T *__restrict__ dx = reinterpret_cast<T *>(a.dx) + row * a.E;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int iv = threadIdx.x + k * TH;
+            if (iv < nvec) {
+                Pack<T, VEC> out;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) out.v[i] = cvt_out<T, float>(rstd * (gg[k][i] - c1 - xh[k][i] * c2));
+                *reinterpret_cast<Pack<T, VEC> *>(dx + (int64_t)iv * VEC) = out;
+            }
+        }
+        mean = mean_n;
+        rstd = rstd_n;
+        if (++st == stages) {
+            st = 0;
+            ph ^= 1;
+        }
+    }
+    float *__restrict__ part = a.dgain_partial + (int64_t)blockIdx.x * a.E;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int iv = threadIdx.x + k * TH;
+        if (iv < nvec) {
+#pragma unroll
+            for (int i = 0; i < VEC; i += 4)
+                *reinterpret_cast<float4 *>(part + (int64_t)iv * VEC + i) = make_float4(dgain[k][i], dgain[k][i + 1], dgain[k][i + 2], dgain[k][i + 3]);
         }
     }
 }
@@ -502,59 +643,58 @@ __global__ void __cluster_dims__(1, CM_C, 1) __launch_bounds__(CM_WARPS * 32) co
     // the row count of a warp does not depend on the column: lanes without a valid column report the count too (uniform merge)
     if (lane == 0) w_n[warp] = r0 < a.R ? (float)((a.R - r0 + rstep - 1) / rstep) : 0.f;
     __syncthreads();
-    if (warp == 0) {
-        float cn = w_n[0];
+    // Fold in two levels, ONE COLUMN PER THREAD (the first version let warp 0 walk all 15 other warps for its VEC columns per lane:
+    // 60 dependent Chan updates, each with a division — 3.7 us of an 18 us kernel).  Level 1: thread (g, c) merges warps 4g .. 4g + 3
+    // of column c (g = 0 .. CM_WARPS / 4 - 1); level 2: threads of group 0 merge the group results.  Fixed order: deterministic.
+    constexpr int NCOL = 32 * VEC, NG = CM_WARPS / 4;
+    static_assert(NCOL * NG <= CM_WARPS * 32, "one (group, column) per thread");
+    const int tc = threadIdx.x % NCOL, tg = threadIdx.x / NCOL;
+    float cn = 0.f, cm = 0.f, cs = 0.f;
+    if (tg < NG) {
+        cn = w_n[4 * tg];
+        cm = w_mean[4 * tg][tc];
+        cs = w_m2[4 * tg][tc];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            mean[i] = w_mean[0][lane * VEC + i];
-            m2[i] = w_m2[0][lane * VEC + i];
-        }
-        for (int w = 1; w < CM_WARPS; ++w) {
-            const float nb = w_n[w];
-            float nn = cn;
+        for (int w = 1; w < 4; ++w) chan_merge(cn, cm, cs, w_n[4 * tg + w], w_mean[4 * tg + w][tc], w_m2[4 * tg + w][tc]);
+    }
+    __syncthreads();  // every partial has been read: rows 0 .. NG - 1 of the arrays are reused for the group results
+    if (tg < NG) {
+        w_mean[tg][tc] = cm;
+        w_m2[tg][tc] = cs;
+        if (tc == 0) w_n[tg] = cn;
+    }
+    __syncthreads();
+    if (tg == 0) {
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                nn = cn;
-                chan_merge(nn, mean[i], m2[i], nb, w_mean[w][lane * VEC + i], w_m2[w][lane * VEC + i]);
-            }
-            cn = nb == 0.f ? cn : nn;
-        }
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            c_mean[lane * VEC + i] = mean[i];
-            c_m2[lane * VEC + i] = m2[i];
-        }
-        if (lane == 0) c_n = cn;
+        for (int g = 1; g < NG; ++g) chan_merge(cn, cm, cs, w_n[g], w_mean[g][tc], w_m2[g][tc]);
+        c_mean[tc] = cm;
+        c_m2[tc] = cs;
+        if (tc == 0) c_n = cn;
     }
     cg::cluster_group cluster = cg::this_cluster();
     cluster.sync();
-    if (cluster.block_rank() == 0 && warp == 0) {
-        float cn = c_n;
+    if (cluster.block_rank() == 0 && tg == 0) {
+        float pn[CM_C], pm[CM_C], ps[CM_C];  // every remote value is requested before the first merge
+#pragma unroll
         for (unsigned rk = 1; rk < CM_C; ++rk) {
-            const float nb = *cluster.map_shared_rank(&c_n, rk);
-            const float *pm = cluster.map_shared_rank(&c_mean[0], rk), *ps = cluster.map_shared_rank(&c_m2[0], rk);
-            float nn = cn;
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                nn = cn;
-                chan_merge(nn, mean[i], m2[i], nb, pm[lane * VEC + i], ps[lane * VEC + i]);
-            }
-            cn = nb == 0.f ? cn : nn;
+            pn[rk] = *cluster.map_shared_rank(&c_n, rk);
+            pm[rk] = cluster.map_shared_rank(&c_mean[0], rk)[tc];
+            ps[rk] = cluster.map_shared_rank(&c_m2[0], rk)[tc];
         }
-        if (col_ok) {
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                float second;
-                if (a.mode == 0) {
-                    second = rsqrtf(m2[i] / (float)a.R + a.eps);
-                } else {
-                    const float div = (float)a.R - 1.f;
-                    second = m2[i] / (div > 0.f ? div : 0.f);
-                    if (a.take_sqrt) second = sqrtf(second);
-                }
-                a.out0[o * a.inner + col0 + i] = mean[i];
-                a.out1[o * a.inner + col0 + i] = second;
+        for (unsigned rk = 1; rk < CM_C; ++rk) chan_merge(cn, cm, cs, pn[rk], pm[rk], ps[rk]);
+        const int64_t col = (int64_t)blockIdx.x * NCOL + tc;
+        if (col < a.inner) {
+            float second;
+            if (a.mode == 0) {
+                second = rsqrtf(cs / (float)a.R + a.eps);
+            } else {
+                const float div = (float)a.R - 1.f;
+                second = cs / (div > 0.f ? div : 0.f);
+                if (a.take_sqrt) second = sqrtf(second);
             }
+            a.out0[o * a.inner + col] = cm;
+            a.out1[o * a.inner + col] = second;
         }
     }
     cluster.sync();  // peers keep their shared memory alive until rank 0 has read it
@@ -586,7 +726,9 @@ int layer_norm_bwd_ctas(int64_t rows, bool write_dx) {
     // KF_LN_BWD=two keeps the two-launch form (A/B runs).
     const char *mode = std::getenv("KF_LN_BWD");
     const bool two = mode && std::strcmp(mode, "two") == 0;
-    const int64_t cap = (int64_t)Runtime::get().props().sm_count * ((write_dx && !two) ? 2 : 8);
+    const char *per_sm = std::getenv("KF_LN_BWD_CTAS");  // tuning hook: resident CTAs per SM of the one-pass kernel
+    const int fused_per_sm = per_sm ? std::max(1, std::atoi(per_sm)) : 2;
+    const int64_t cap = (int64_t)Runtime::get().props().sm_count * ((write_dx && !two) ? fused_per_sm : 8);
     return (int)std::max<int64_t>(1, std::min<int64_t>(rows, cap));
 }
 
@@ -596,10 +738,27 @@ static void ln_bwd_typed(const LnArgs &a, int ctas, bool write_dx) {
     Runtime &rt = Runtime::get();
     const char *mode = std::getenv("KF_LN_BWD");
     const bool two = mode && std::strcmp(mode, "two") == 0;
+    const bool narrow = mode && std::strcmp(mode, "narrow") == 0;  // KF_LN_BWD=narrow: 128 threads x 8 vectors (A/B runs)
+    // default: rows streamed through a shared-memory ring (KF_LN_BWD=regs keeps the register-prefetch kernel); 96 KB of ring per CTA
+    const int64_t row_bytes = a.E * (int64_t)sizeof(T);
+    const int ring_stages = (int)std::min<int64_t>(8, 98304 / (2 * row_bytes));
+    const bool ring = !mode && ring_stages >= 2 && row_bytes % 16 == 0 && reinterpret_cast<uintptr_t>(a.dy) % 16 == 0;
 #define KF_LN_BWD(NVV)                                                                                                          \
     do {                                                                                                                        \
+        if (write_dx && ring && ((NVV + 1) / 2) * VEC <= 16) { /* 32 columns per thread (16-bit rows of 8192) would spill */    \
+            constexpr int NVR = (NVV + 1) / 2; /* 256 threads: half the vectors per thread */                                   \
+            static bool attr_done = false;                                                                                      \
+            if (!attr_done) {                                                                                                   \
+                KF_CUDA(cudaFuncSetAttribute(layer_norm_bwd_ring_kernel<T, VEC, NVR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304)); \
+                attr_done = true;                                                                                               \
+            }                                                                                                                   \
+            layer_norm_bwd_ring_kernel<T, VEC, NVR><<<ctas, 256, (size_t)(ring_stages * 2 * row_bytes), rt.stream()>>>(a, ring_stages); \
+            break;                                                                                                              \
+        }                                                                                                                       \
         if (write_dx && !two) {                                                                                                 \
-            layer_norm_bwd_fused_kernel<T, VEC, NVV><<<ctas, LN_THREADS, 0, rt.stream()>>>(a);                                  \
+            /* 8 vectors per thread at 128 threads: 256 threads hold 4 each (211 -> ~110 registers, twice the warps per SM) */  \
+            if (NVV == 8 && !narrow) layer_norm_bwd_fused_kernel<T, VEC, (NVV + 1) / 2, 256><<<ctas, 256, 0, rt.stream()>>>(a);  \
+            else layer_norm_bwd_fused_kernel<T, VEC, NVV, LN_THREADS><<<ctas, LN_THREADS, 0, rt.stream()>>>(a);                  \
             break;                                                                                                              \
         }                                                                                                                       \
         if (write_dx) {                                                                                                         \

@@ -37,6 +37,8 @@ struct AttnBwdTcParams {
     float scale;         // softmax scale (applied to dK / dQ in the epilogue)
     int nblk;            // 128-row blocks of the stationary operand per (b, h)
     int is_bf16;
+    int hg;              // heads per scheduling group: inside a group the CTAs run weight-major (every head's heaviest block first,
+                         // longest-processing-time order), at most hg heads' streamed operands live in L2 at a time
 };
 
 __device__ __forceinline__ uint32_t pack16b(float a, float b, int is_bf16) {
@@ -161,8 +163,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_con
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bh = blockIdx.x / p.nblk;
-    const int blk = MODE == MODE_DKV ? (blockIdx.x % p.nblk) : (p.nblk - 1 - (blockIdx.x % p.nblk));  // heaviest blocks first
+    int bh, blk;
+    {
+        const int per_group = p.hg * p.nblk;
+        const int g = blockIdx.x / per_group, idx = blockIdx.x - g * per_group;
+        const int heads = min(p.hg, (int)p.BH - g * p.hg);  // the last group may be partial
+        const int lvl = idx / heads;                         // 0 = heaviest
+        bh = g * p.hg + (idx - lvl * heads);
+        blk = MODE == MODE_DKV ? lvl : (p.nblk - 1 - lvl);
+    }
     const int x0_row = blk * 128;
     // streamed 64-row tiles [t_lo, t_hi)
     int t_lo, t_hi;
@@ -417,6 +426,12 @@ static void launch_bwd_mode(const AttnBwdPlan &a, const float *lse2, const float
     p.scale_log2 = (float)(scale * 1.4426950408889634);
     p.nblk = (int)(((MODE == MODE_DKV ? a.Skv : a.Sq) + 127) / 128);
     p.is_bf16 = bf16;
+    {  // heads per scheduling group.  Measured at C3 and at S = 1024 (tools/gpu_attn_bwd_ab.py): unlike the forward, the backward
+       // is no faster in weight-major order (groups that fit the L2, or one global list) than head-major, so 1 stays the default
+        int64_t hg = 1;
+        if (const char *e = std::getenv("KF_ATTN_HG")) hg = std::max(1, std::atoi(e));
+        p.hg = (int)std::min<int64_t>(hg, a.BH);
+    }
     constexpr int SMEM = 2 * 128 * D * 2 + AB_NSTAGE * 2 * 64 * D * 2 + 2 * 2 * 128 * 4 + 256 + 1024;
     auto kern = attn_bwd_tc_kernel<D, MODE>;
     static bool attr_done = false;

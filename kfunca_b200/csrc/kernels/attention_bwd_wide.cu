@@ -55,6 +55,7 @@ struct WParams {
     float scale;         // softmax scale (applied to dK / dQ in the epilogue)
     int nblk;            // 128-row blocks of the stationary operand per (b, h)
     int is_bf16;
+    int hg, BH;          // heads per scheduling group (weight-major inside a group, see attention_bwd_tc.cu) / batch-heads
     long long *trace;    // KF_ATTN_TRACE=1: clock64() stamps of CTA 0's pipeline events, [tile][16]; null otherwise
 };
 #define W_TRACE(n, k)                                                                                   \
@@ -262,8 +263,15 @@ attn_bwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_c
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ds_free + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bh = blockIdx.x / p.nblk;
-    const int blk = MODE == W_DKV ? (blockIdx.x % p.nblk) : (p.nblk - 1 - (blockIdx.x % p.nblk));  // heaviest blocks first
+    int bh, blk;
+    {
+        const int per_group = p.hg * p.nblk;
+        const int g = blockIdx.x / per_group, idx = blockIdx.x - g * per_group;
+        const int heads = min(p.hg, p.BH - g * p.hg);  // the last group may be partial
+        const int lvl = idx / heads;                    // 0 = heaviest
+        bh = g * p.hg + (idx - lvl * heads);
+        blk = MODE == W_DKV ? lvl : (p.nblk - 1 - lvl);
+    }
     const int b_idx = bh / p.H, h_idx = bh % p.H;
     const int x0_row = blk * 128;
     int t_lo, t_hi;  // streamed 128-row tiles [t_lo, t_hi)
@@ -582,6 +590,13 @@ void launch_wide_mode(const AttnBwdPlan &a, const WLayouts &L, const float *nlse
     p.scale_log2 = (float)(scale * 1.4426950408889634);
     p.nblk = (int)(((MODE == W_DKV ? a.Skv : a.Sq) + 127) / 128);
     p.is_bf16 = bf16;
+    {  // heads per scheduling group.  Measured at C3 and at S = 1024 (tools/gpu_attn_bwd_ab.py): unlike the forward, the backward
+       // is no faster in weight-major order (groups that fit the L2, or one global list) than head-major, so 1 stays the default
+        int64_t hg = 1;
+        if (const char *e = std::getenv("KF_ATTN_HG")) hg = std::max(1, std::atoi(e));
+        p.hg = (int)std::min<int64_t>(hg, a.BH);
+        p.BH = (int)a.BH;
+    }
     static const bool want_trace = std::getenv("KF_ATTN_TRACE") != nullptr;
     Scratch trace_buf(want_trace ? 64 * 24 * 8 : 16);
     p.trace = nullptr;

@@ -44,10 +44,23 @@ struct AttnTcParams {
     int is_bf16;
     int H;             // heads per batch entry: (b, h) = (bh / H, bh % H) for the 4-D tensor maps and the output layout
     AttnLayout lo;     // layout of `out`
-    int early_s;       // persistent kernel: 1 = tile 0's first S of the next item is issued during the item's last (tile-1-only) block
+    int hg;            // heads per scheduling group (see fwd_decode_item)
+    unsigned int *work_counter;  // persistent kernel: items claimed beyond the first one of every CTA (zeroed before the launch)
     int stale;         // 1: blocks after the first take their exponentials relative to the running reference (fwd_softmax_block_stale)
     long long *trace;  // KF_ATTN_TRACE=1 (persistent kernel): clock64() stamps of CTA 0, [256 blocks][16] + [64 items][4] at 4096; else null
 };
+
+// Work item w -> (batch-head, query pair).  Heads are taken in groups of p.hg (a group's K and V fit in L2 together); inside a group
+// the items run length-major: every head's longest pair first, then the next length ... — longest-processing-time order for the
+// load balance, at most hg heads' K / V live at a time for the L2.  hg = BH: one global length-major list; hg = 1: head-major.
+__device__ __forceinline__ void fwd_decode_item(const AttnTcParams &p, const int w, int &bh, int &pr) {
+    const int per_group = p.hg * p.npairs;
+    const int g = w / per_group, idx = w - g * per_group;
+    const int heads = min(p.hg, (int)p.BH - g * p.hg);  // the last group may be partial
+    const int lvl = idx / heads;
+    bh = g * p.hg + (idx - lvl * heads);
+    pr = p.npairs - 1 - lvl;
+}
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
@@ -479,9 +492,9 @@ __device__ __forceinline__ void attn_fwd_tc_body(const CUtensorMap &tmap_q, cons
     float *xch = reinterpret_cast<float *>(smem + (2 + NS) * TILE_BYTES + 256);  // [tile][half][parity][row] row-max / row-sum exchange (NH = 2)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bh = blockIdx.x / p.npairs;
+    int bh, pr;
+    fwd_decode_item(p, (int)blockIdx.x, bh, pr);  // heaviest (longest KV range) pairs of a head group first
     const int b_idx = bh / p.H, h_idx = bh % p.H;
-    const int pr = p.npairs - 1 - (blockIdx.x % p.npairs);  // heaviest (longest KV range) pairs first
     const int q0 = pr * 2 * FA_BQ;
     auto blocks_of = [&](int t) {
         const int64_t q0t = (int64_t)q0 + t * FA_BQ;
@@ -1035,10 +1048,10 @@ attn_fwd_ps_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 }
 
 // =====================================================================================================================
-// Forward, PERSISTENT form (KF_ATTN_FWD=pers; the default for KV lengths <= 2048): one CTA per SM walks a static list of (batch-head, query pair) work items, heaviest pairs
-// first (longest-processing-time order: all pairs of the longest KV range over every batch-head, then the next length, ...; CTA c
-// takes items c, c + grid, c + 2 grid, ... so every CTA sees the same length profile).  The roles are those of attn_fwd_tc_body
-// (NH = 1), but the K/V ring, the TMEM allocation, the tensor maps and the barrier set-up outlive a work item:
+// Forward, PERSISTENT form (KF_ATTN_FWD=pers; the default for KV lengths <= 2048): one CTA per SM takes (batch-head, query pair)
+// work items from a dynamic queue (see get_item below) in the order of fwd_decode_item: head groups that fit the L2, longest pairs
+// first inside a group.  The roles are those of attn_fwd_tc_body (NH = 1), but the K/V ring, the TMEM allocation, the tensor maps
+// and the barrier set-up outlive a work item:
 //   * the TMA warp loads the next item's Q tiles as soon as the last S MMA of the current item has completed (q_empty) and keeps
 //     the K/V ring running across the item boundary, so a new item never waits for cold loads;
 //   * the MMA warp issues S_0, S_1 of the next item straight after the last P V of the current one: they run under the epilogue;
@@ -1068,18 +1081,28 @@ attn_fwd_pers_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     uint64_t *p_full = s_full + 2;         // [2 tiles][2 key halves]
     uint64_t *o_full = p_full + 4;         // [2]: every P V of the item has completed
     uint64_t *o_free = o_full + 2;         // [2]: the epilogue has read O out of tensor memory
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_free + 2);
+    uint64_t *work_full = o_free + 2;      // [4]: the producer has published the work item of this queue slot
+    uint64_t *work_empty = work_full + 4;  // [4]: the MMA warp and the eight softmax warps have read it
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(work_empty + 4);
+    volatile int *work = reinterpret_cast<volatile int *>(tmem_slot + 1);  // [4] item index, -1 = no more work
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwork = (int)p.BH * p.npairs;
-    // round r of the static schedule: CTA c takes item r G + c in even rounds and r G + (G - 1 - c) in odd ones (G = grid).  The list is
-    // sorted by decreasing length, so a plain stride-G walk hands the CTAs that straddle a length step the longer item in EVERY
-    // round they straddle one (up to one longest item, 7 % of a CTA's work at S = 4096); the boustrophedon cancels it pairwise.
-    auto item_of = [&](int r) {
-        const int w = r * (int)gridDim.x + ((r & 1) ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x);
-        return w < nwork ? w : -1;
+    // Work items are handed out DYNAMICALLY in head-major order (item w = pair npairs - 1 - w % npairs of batch-head w / npairs: a
+    // head's pairs longest first, then the next head), the order the hardware scheduler gives the per-CTA kernel.  CTA c starts with
+    // item c; its producer thread claims every further item from a global counter (one atomicAdd per item, issued before the item's
+    // Q loads so the round trip is hidden) and publishes it through a four-slot queue in shared memory.  A static length-major list
+    // (every head's longest pair first) balances as well but has all 148 CTAs streaming the K / V of 148 DIFFERENT heads at once:
+    // 296 MB of live K / V at S = 4096 against 126 MB of L2, i.e. 64 KB per SM and block from HBM — the kernel ran at the HBM limit
+    // (measured 1.12 ms at C3 against 1.03 ms for the per-CTA kernel, which keeps ~5 heads live).
+    auto get_item = [&](int it) {  // consumers (whole warp): the it-th item of this CTA
+        const int sl = it & 3;
+        mbar_wait(&work_full[sl], (uint32_t)((it >> 2) & 1));
+        const int w = work[sl];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&work_empty[sl]);
+        return w;
     };
-    // work item w -> (batch-head, pair): pairs in decreasing length, every batch-head of a length before the next length
     auto blocks_of = [&](int q0, int t) {
         const int64_t q0t = (int64_t)q0 + t * FA_BQ;
         const int64_t kv_end = min((int64_t)p.Skv, q0t + FA_BQ);
@@ -1093,6 +1116,10 @@ attn_fwd_pers_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         prefetch_tmap(&tmap_o);
         mbar_init(q_full, 1);
         mbar_init(q_empty, 1);
+        for (int sl = 0; sl < 4; ++sl) {
+            mbar_init(&work_full[sl], 1);
+            mbar_init(&work_empty[sl], 9);
+        }
         for (int s = 0; s < NS; ++s) {
             mbar_init(&kv_full[s], 1);
             mbar_init(&kv_empty[s], 1);
@@ -1119,8 +1146,24 @@ attn_fwd_pers_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         if (lane == 0) {
             int s = 0, it = 0;
             uint32_t ph = 0;
-            for (int w = item_of(0); w >= 0; w = item_of(++it)) {
-                const int bh = w % (int)p.BH, pr = p.npairs - 1 - w / (int)p.BH;
+            auto claim = [&]() {
+                const int c = (int)atomicAdd(p.work_counter, 1u) + (int)gridDim.x;
+                return c < nwork ? c : -1;
+            };
+            auto publish = [&](int idx, int item) {  // queue slot free once the nine consumer warps have read its previous content
+                const int sl = idx & 3;
+                mbar_wait(&work_empty[sl], (uint32_t)(((idx >> 2) & 1) ^ 1));
+                work[sl] = item;
+                mbar_arrive(&work_full[sl]);
+            };
+            int w = (int)blockIdx.x;  // grid <= nwork
+            publish(0, w);
+            int wn = claim();  // the only claim whose round trip is exposed (once per CTA)
+            publish(1, wn);
+            for (; w >= 0; ++it) {
+                const int wnn = claim();  // item it + 2: claimed two items ahead, used (published) at the end of this item's loads
+                int bh, pr;
+                fwd_decode_item(p, w, bh, pr);
                 const int b_idx = bh / p.H, h_idx = bh % p.H, q0 = pr * 2 * FA_BQ;
                 const int nblk0 = blocks_of(q0, 0), nblk1 = blocks_of(q0, 1), nmax = max(nblk0, nblk1);
                 const int ntile_q = nblk1 > 0 ? 2 : 1;
@@ -1141,6 +1184,9 @@ attn_fwd_pers_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                         ph ^= 1;
                     }
                 }
+                publish(it + 2, wnn);
+                w = wn;
+                wn = wnn;
             }
         }
         __syncwarp();
@@ -1178,26 +1224,23 @@ attn_fwd_pers_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         };
         uint32_t cp0 = 0, cp1 = 0;    // blocks of tile 0 / 1 handed over so far (phase of p_full)
         uint32_t act0 = 0, act1 = 0;  // items in which tile 0 / 1 was active so far (phase of o_free)
-        int early_sk = -1;  // >= 0: S_0 of tile 0 of this item was issued during the previous item's last block, from this ring slot
-        for (int w = item_of(0); w >= 0; w = item_of(++it)) {
-            const int pr = p.npairs - 1 - w / (int)p.BH, q0 = pr * 2 * FA_BQ;
+        for (int w = get_item(0); w >= 0; w = get_item(++it)) {
+            int bh_unused, pr;
+            fwd_decode_item(p, w, bh_unused, pr);
+            const int q0 = pr * 2 * FA_BQ;
             const int nblk0 = blocks_of(q0, 0), nblk1 = blocks_of(q0, 1), nmax = max(nblk0, nblk1);
             {
-                int sk = early_sk;
-                if (sk < 0) {
-                    mbar_wait(q_full, (uint32_t)(it & 1));
-                    sk = next_slot();  // K_0
-                }
+                mbar_wait(q_full, (uint32_t)(it & 1));
+                const int sk = next_slot();  // K_0
                 tc_fence_after();
 #pragma unroll
                 for (int t = 0; t < 2; ++t)
-                    if ((t ? nblk1 : nblk0) > 0 && !(t == 0 && early_sk >= 0)) {
+                    if ((t ? nblk1 : nblk0) > 0) {
                         issue_s(t, kv_addr + sk * TILE_BYTES);
                         umma_commit_p(&s_full[t], leader);
                     }
                 umma_commit_p(&kv_empty[sk], leader);
                 if (nmax == 1) umma_commit_p(q_empty, leader);
-                early_sk = -1;
             }
             for (int j = 1; j <= nmax; ++j) {
                 const bool tri = trace != nullptr && blockIdx.x == 0 && cp1 < 256 && leader;
@@ -1207,16 +1250,6 @@ attn_fwd_pers_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 const bool has_k = j < nmax;
                 const int sk = has_k ? next_slot() : 0;  // K_j
                 if (tri) trace[cp1 * 16 + 14] = clock64();
-                if (p.early_s && !has_k && nblk0 < nmax && item_of(it + 1) >= 0) {
-                    // the item's last block belongs to tile 1 alone (the diagonal): tile 0 would idle through it and through tile 1's
-                    // hand-over.  Its first S of the NEXT item is issued now (Q and K_0 of that item are already on their way: q_empty
-                    // was committed with the last S of this item), so tile 0 leaves its epilogue straight into the next item.
-                    mbar_wait(q_full, (uint32_t)((it + 1) & 1));
-                    early_sk = next_slot();
-                    tc_fence_after();
-                    issue_s(0, kv_addr + early_sk * TILE_BYTES);
-                    umma_commit_p(&s_full[0], leader);
-                }
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
                     const int nb_t = t ? nblk1 : nblk0;
@@ -1264,8 +1297,9 @@ attn_fwd_pers_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const float sc = p.scale_log2;
         uint32_t cs = 0, co = 0;  // completions of s_full[t] / o_full[t] consumed so far
         int it = 0;
-        for (int w = item_of(0); w >= 0; w = item_of(++it)) {
-            const int bh = w % (int)p.BH, pr = p.npairs - 1 - w / (int)p.BH;
+        for (int w = get_item(0); w >= 0; w = get_item(++it)) {
+            int bh, pr;
+            fwd_decode_item(p, w, bh, pr);
             const int b_idx = bh / p.H, h_idx = bh % p.H, q0 = pr * 2 * FA_BQ;
             const int n_t = blocks_of(q0, t);
             if (n_t == 0) continue;
@@ -1358,12 +1392,14 @@ static void launch_fwd_tc(const AttnPlan &a) {
         p.stale = (st && st[0] == '1') ? 1 : 0;
     }
     p.trace = nullptr;
-    {
-        const char *es = std::getenv("KF_ATTN_EARLY");  // read per call (A/B runs)
-        p.early_s = (es && es[0] == '1') ? 1 : 0;  // measured: no gain (the next Q arrives too late for the issuer not to stall), off by default
+    {  // heads per scheduling group: as many as keep K + V of the group within ~half of the L2 (KF_ATTN_HG overrides, read per call)
+        const int64_t kv_bytes = 2 * a.Skv * D * 2;
+        int64_t hg = std::max<int64_t>(1, (int64_t)(rt.props().l2_bytes / 2) / std::max<int64_t>(1, kv_bytes));
+        if (const char *e = std::getenv("KF_ATTN_HG")) hg = std::max(1, std::atoi(e));
+        p.hg = (int)std::min<int64_t>(hg, a.BH);
     }
     if constexpr (NH == 4) {  // persistent kernel: one CTA per SM over the longest-first work list
-        constexpr int SMEM_P = (2 + FA_NSTAGE) * 128 * D * 2 + 2 * 128 * 128 + 256 + 1024;  // tiles + epilogue staging + barriers + alignment slack
+        constexpr int SMEM_P = (2 + FA_NSTAGE) * 128 * D * 2 + 2 * 128 * 128 + 512 + 1024;  // tiles + epilogue staging + barriers, work queue + alignment slack
         static bool attr_p = false;
         if (!attr_p) {
             KF_CUDA(cudaFuncSetAttribute(attn_fwd_pers_kernel<D, POLY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_P));
@@ -1381,6 +1417,9 @@ static void launch_fwd_tc(const AttnPlan &a) {
             p.trace = trace_buf.as<long long>();
         }
         const int64_t grid = std::min<int64_t>(nwork, rt.props().sm_count);
+        Scratch counter(16);
+        rt.memset_async(counter.p, 0, 16);
+        p.work_counter = counter.as<unsigned int>();
         if constexpr (D == 128 && POLY == 2) {
             if (want_trace) attn_fwd_pers_kernel<D, POLY, true><<<(unsigned)grid, FaCfg<1>::THREADS, SMEM_P, rt.stream()>>>(tq, tk, tv, to, p);
             else attn_fwd_pers_kernel<D, POLY, false><<<(unsigned)grid, FaCfg<1>::THREADS, SMEM_P, rt.stream()>>>(tq, tk, tv, to, p);
@@ -1455,12 +1494,13 @@ bool launch_attention_fwd_tc(const AttnPlan &a) {
     // threads per row 1.34 ms (818 TFLOP/s) — the extra named barrier, doubled polling and 96-register budget cost more than the
     // shorter dependent chains gain, so KF_ATTN_SPLIT=2 stays an opt-in experiment
     static const int nh = std::getenv("KF_ATTN_SPLIT") ? std::atoi(std::getenv("KF_ATTN_SPLIT")) : 1;
-    // KF_ATTN_FWD (read per call): "pers" = persistent kernel (one CTA per SM over a longest-first work list), "cta" = one CTA per
-    // query pair, "ps" = P through shared memory with the next S issued early; unset = by KV length.  Measured with the two kernels
-    // alternating call by call (gpurun_out/r4b_fwd_ab.log, B H S constant, median ms): S = 1024 0.436 (pers) / 0.470 (cta), 2048
-    // 0.646 / 0.651, 4096 1.117 / 1.030, 8192 2.085 / 2.094, 16384 4.187 / 4.128.  Long runs are power-capped (the first six calls
-    // at S = 16384 take 3.46 ms = 1270 TFLOP/s, later ones 4.2 ms for either kernel), so the choice only matters for short items,
-    // where the persistent kernel's kept-alive ring, barriers and tensor-memory allocation win.
+    // KF_ATTN_FWD (read per call): "pers" = persistent kernel (one CTA per SM, dynamic work queue), "cta" = one CTA per query pair,
+    // "ps" = P through shared memory with the next S issued early; unset = by KV length.  Both kernels walk the items in the order
+    // of fwd_decode_item.  Measured with the variants alternating call by call (gpurun_out/r6c_fwd_ab.log, B H S constant, fastest
+    // call in ms, persistent / per-CTA): S = 1024 0.388 / 0.421 (head-major order: 0.478 / 0.479), 2048 0.600 / 0.624, 4096
+    // 1.016 / 1.026, 8192 1.880 / 1.821, 16384 equal within the power-cap noise (the first ~20 ms of a series run at 1270 TFLOP/s,
+    // later calls at ~1050 for either kernel).  The persistent kernel's kept-alive ring, barriers and tensor-memory allocation
+    // pay for short items; for long ones the per-CTA kernel is as fast and simpler.
     const char *fwd_mode = std::getenv("KF_ATTN_FWD");
     const bool ps = fwd_mode && std::strcmp(fwd_mode, "ps") == 0;
     const bool per_cta = fwd_mode ? std::strcmp(fwd_mode, "pers") != 0 : a.Skv > 2048;

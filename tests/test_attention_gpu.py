@@ -52,6 +52,23 @@ def test_attention_against_reference_outputs(name):
     np.testing.assert_allclose(out, GOLD[f"{name}.out"], rtol=2e-5, atol=2e-5)
 
 
+@pytest.mark.parametrize("kernel", ["pers", "cta"])
+@pytest.mark.parametrize("hg", ["1", "4", "7", "1000000"])
+@pytest.mark.parametrize("shape", [(3, 5, 130, 130, 128), (2, 9, 513, 257, 64), (1, 30, 300, 700, 128)])
+def test_forward_kernels_and_item_orders_agree(kernel, hg, shape, monkeypatch):
+    """Both forward kernels (persistent work queue / one CTA per query pair) under every scheduling order (heads per group: one,
+    partial last group, all) give the bits of the default path: the order only decides which CTA computes an item."""
+    q, k, v = (to16(t, "bf16") for t in qkv(*shape))
+    gq, gk, gv = g(q), g(k), g(v)
+    ref_o, ref_l = kf.causal_attention_fwd(gq, gk, gv)
+    ref_o, ref_l = ref_o.float().numpy(), ref_l.numpy()
+    monkeypatch.setenv("KF_ATTN_FWD", kernel)
+    monkeypatch.setenv("KF_ATTN_HG", hg)
+    o, l = kf.causal_attention_fwd(gq, gk, gv)
+    assert np.array_equal(o.float().numpy(), ref_o) and np.array_equal(l.numpy(), ref_l)
+    np.testing.assert_allclose(ref_o, O.causal_attention(q, k, v), rtol=2e-2, atol=1e-2)
+
+
 @pytest.mark.parametrize("dt", ["bf16", "fp16"])
 @pytest.mark.parametrize("shape", [(1, 2, 128, 128, 128), (2, 3, 256, 256, 64), (1, 2, 384, 384, 128), (2, 2, 200, 333, 128),
                                    (1, 1, 130, 70, 64), (1, 4, 1024, 1024, 128)])

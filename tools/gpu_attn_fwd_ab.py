@@ -67,12 +67,16 @@ for S in () if TRACE_ONLY else (1024, 2048, 4096, 8192, 16384):
     fl = 4 * B * H * S * S * D / 2
     # the two kernels alternate call by call (the GPU is power-capped: clocks drift by 10 - 20 % over tens of milliseconds, so
     # back-to-back windows of one variant each are not comparable); per variant: minimum and median over the calls
-    times = {"pers": [], "pers-early": [], "cta": []}
+    times = {f"{m}:{hg}": [] for m in ("pers", "cta") for hg in ("1", "auto", "all")}  # heads per scheduling group (KF_ATTN_HG)
     evs = [Event() for _ in range(3)]
-    for rep in range(24):
+    for rep in range(16):
         for mode in times:
-            os.environ["KF_ATTN_FWD"] = mode.split("-")[0]
-            os.environ["KF_ATTN_EARLY"] = "1" if mode.endswith("early") else "0"
+            os.environ["KF_ATTN_FWD"] = mode.split(":")[0]
+            hg = mode.split(":")[1]
+            if hg == "auto":
+                os.environ.pop("KF_ATTN_HG", None)
+            else:
+                os.environ["KF_ATTN_HG"] = "1" if hg == "1" else "1000000"
             if rep < 2:
                 kf.causal_attention_fwd(Q, K, V)
                 continue
@@ -82,7 +86,8 @@ for S in () if TRACE_ONLY else (1024, 2048, 4096, 8192, 16384):
             evs[1].synchronize()
             times[mode].append(evs[0].elapsed_ms(evs[1]))
     res = [f"{m} min {min(t):.3f} med {sorted(t)[len(t) // 2]:.3f} ms {fl / sorted(t)[len(t) // 2] / 1e9:7.1f} TFLOP/s" for m, t in times.items()]
-    print(f"B={B} S={S}: " + " | ".join(res), flush=True)
+    print(f"B={B} S={S}:\n    " + "\n    ".join(res), flush=True)
+    os.environ.pop("KF_ATTN_HG", None)
     if "--all" in sys.argv:
         for m, t in times.items():
             print(f"    {m}: " + " ".join(f"{x:.3f}" for x in t), flush=True)

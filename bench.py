@@ -533,9 +533,9 @@ def per_config(kf, Event, peaks, ref_cfg):
         A[i].zero_grad()
         ys[i].backward(B[i])
 
-    # through the autograd engine: dx kernel + gain-gradient kernel + partial fold + the engine's copy of dx into the leaf's
-    # grad slot; the algorithmic bytes counted are only x, dy in and dx out
-    mem("f1_layer_norm_bwd_autograd_fp32_4096", ln_bwd, 3 * nb, "layer_norm_bwd_kernel x2 + fold")
+    # through the autograd engine: the one-pass ring kernel (dx + gain-gradient partials) + the partial fold; the algorithmic
+    # bytes counted are only x, dy in and dx out
+    mem("f1_layer_norm_bwd_autograd_fp32_4096", ln_bwd, 3 * nb, "layer_norm_bwd_ring_kernel + reduce_cols_kernel (partial fold)")
     # embedding gather, 32768 tokens x 4096 bf16 from a 32000-row table (read ids + rows, write rows)
     V, E, ntok = 32000, 4096, 32768
     table = kf.empty([V, E], kf.bfloat16, 0)

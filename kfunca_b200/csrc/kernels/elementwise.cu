@@ -47,6 +47,7 @@ constexpr int kPack = 8;
 
 template <int OP, int ACC, int NIN, int SDT>
 __global__ void __launch_bounds__(256) ew_pack_kernel(const EwPlan p, const int64_t npacks, const uint32_t inner_packs) {
+    pdl_enter();
     using A = typename AccType<ACC>::type;
     const int dt0 = SDT >= 0 ? SDT : p.dtype[0];
     const int dt1 = SDT >= 0 ? SDT : p.dtype[1];
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(256) ew_pack_kernel(const EwPlan p, const int6
 
 template <int OP, int ACC, int NIN, typename IndexT>
 __global__ void __launch_bounds__(256) ew_scalar_kernel(const EwPlan p) {
+    pdl_enter();
     using A = typename AccType<ACC>::type;
     constexpr int U = 4;
     const A sval = static_cast<A>(p.scalar);
@@ -176,21 +178,21 @@ static void launch_typed(const EwPlan &p) {
         const int grid = grid_for(npacks, 256, 8);
         const bool same = (NIN < 1 || p.dtype[1] == p.dtype[0]) && (NIN < 2 || p.b_is_scalar || p.dtype[2] == p.dtype[0]);
         if (ACC == ACC_F32 && same && p.dtype[0] == KF_FLOAT)
-            ew_pack_kernel<OP, ACC, NIN, KF_FLOAT><<<grid, 256, 0, st>>>(p, npacks, inner_packs);
+            launch_pdl(ew_pack_kernel<OP, ACC, NIN, KF_FLOAT>, dim3(grid), dim3(256), 0, st, p, npacks, inner_packs);
         else if (ACC == ACC_F32 && same && p.dtype[0] == KF_BFLOAT16)
-            ew_pack_kernel<OP, ACC, NIN, KF_BFLOAT16><<<grid, 256, 0, st>>>(p, npacks, inner_packs);
+            launch_pdl(ew_pack_kernel<OP, ACC, NIN, KF_BFLOAT16>, dim3(grid), dim3(256), 0, st, p, npacks, inner_packs);
         else if (ACC == ACC_F32 && same && p.dtype[0] == KF_HALF)
-            ew_pack_kernel<OP, ACC, NIN, KF_HALF><<<grid, 256, 0, st>>>(p, npacks, inner_packs);
+            launch_pdl(ew_pack_kernel<OP, ACC, NIN, KF_HALF>, dim3(grid), dim3(256), 0, st, p, npacks, inner_packs);
         else
-            ew_pack_kernel<OP, ACC, NIN, -1><<<grid, 256, 0, st>>>(p, npacks, inner_packs);
+            launch_pdl(ew_pack_kernel<OP, ACC, NIN, -1>, dim3(grid), dim3(256), 0, st, p, npacks, inner_packs);
         rt.post_launch("ew_pack_kernel");
         return;
     }
     const int grid = grid_for((p.numel + 3) / 4, 256, 8);
     if (p.numel < (int64_t)0x7FFFFFFF)
-        ew_scalar_kernel<OP, ACC, NIN, uint32_t><<<grid, 256, 0, st>>>(p);
+        launch_pdl(ew_scalar_kernel<OP, ACC, NIN, uint32_t>, dim3(grid), dim3(256), 0, st, p);
     else
-        ew_scalar_kernel<OP, ACC, NIN, uint64_t><<<grid, 256, 0, st>>>(p);
+        launch_pdl(ew_scalar_kernel<OP, ACC, NIN, uint64_t>, dim3(grid), dim3(256), 0, st, p);
     rt.post_launch("ew_scalar_kernel");
 }
 

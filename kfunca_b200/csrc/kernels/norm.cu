@@ -61,6 +61,7 @@ struct LnArgs {
 // occupancy, more loads in flight per SM)
 template <typename T, int VEC, int NV, int TH>
 __global__ void __launch_bounds__(TH) layer_norm_fwd_kernel(const LnArgs a) {
+    pdl_enter();
     __shared__ float red[16];
     const int64_t row = blockIdx.x;
     const int nvec = (int)(a.E / VEC);
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(TH) layer_norm_fwd_kernel(const LnArgs a) {
 template <typename T, int VEC, int NV, int TH>
 __global__ void __launch_bounds__(TH) row_moments_kernel(const T *__restrict__ xin, T *__restrict__ out_mean, T *__restrict__ out_var,
                                                                  const int64_t E, const int take_sqrt) {
+    pdl_enter();
     __shared__ float red[16];
     const int64_t row = blockIdx.x;
     const int nvec = (int)(E / VEC);
@@ -359,6 +361,7 @@ __global__ void __launch_bounds__(TH, 2) layer_norm_bwd_fused_kernel(const LnArg
 // The gain and the gain-gradient sums of a thread's columns live in registers for the whole kernel.
 template <typename T, int VEC, int NV>
 __global__ void __launch_bounds__(256, 2) layer_norm_bwd_ring_kernel(const LnArgs a, const int stages) {
+    pdl_enter();
     constexpr int TH = 256, NW = TH / 32;
     extern __shared__ __align__(128) unsigned char ring_raw[];
     __shared__ float red[2][2 * NW];
@@ -506,10 +509,10 @@ static void ln_fwd_typed(const LnArgs &a) {
     KF_CHECK(a.rows < (int64_t)0x7FFFFFFF);
     const unsigned grid = (unsigned)a.rows;
     switch (ln_nv<T>(a.E)) {
-    case 1: layer_norm_fwd_kernel<T, VEC, 1, LN_THREADS><<<grid, LN_THREADS, 0, rt.stream()>>>(a); break;
-    case 2: layer_norm_fwd_kernel<T, VEC, 2, LN_THREADS><<<grid, LN_THREADS, 0, rt.stream()>>>(a); break;
-    case 4: layer_norm_fwd_kernel<T, VEC, 4, LN_THREADS><<<grid, LN_THREADS, 0, rt.stream()>>>(a); break;
-    default: layer_norm_fwd_kernel<T, VEC, 4, 256><<<grid, 256, 0, rt.stream()>>>(a); break;  // 8 vectors per thread at 128 = 4 at 256
+    case 1: launch_pdl(layer_norm_fwd_kernel<T, VEC, 1, LN_THREADS>, dim3(grid), dim3(LN_THREADS), 0, rt.stream(), a); break;
+    case 2: launch_pdl(layer_norm_fwd_kernel<T, VEC, 2, LN_THREADS>, dim3(grid), dim3(LN_THREADS), 0, rt.stream(), a); break;
+    case 4: launch_pdl(layer_norm_fwd_kernel<T, VEC, 4, LN_THREADS>, dim3(grid), dim3(LN_THREADS), 0, rt.stream(), a); break;
+    default: launch_pdl(layer_norm_fwd_kernel<T, VEC, 4, 256>, dim3(grid), dim3(256), 0, rt.stream(), a); break;  // 8 vectors per thread at 128 = 4 at 256
     }
     rt.post_launch("layer_norm_fwd_kernel");
 }
@@ -534,10 +537,10 @@ bool launch_row_moments(const void *x, void *mean, void *var, int dtype, int64_t
     float *mp = reinterpret_cast<float *>(mean), *vp = reinterpret_cast<float *>(var);
     const unsigned grid = (unsigned)rows;
     switch (ln_nv<float>(E)) {
-    case 1: row_moments_kernel<float, 4, 1, LN_THREADS><<<grid, LN_THREADS, 0, rt.stream()>>>(xp, mp, vp, E, take_sqrt); break;
-    case 2: row_moments_kernel<float, 4, 2, LN_THREADS><<<grid, LN_THREADS, 0, rt.stream()>>>(xp, mp, vp, E, take_sqrt); break;
-    case 4: row_moments_kernel<float, 4, 4, LN_THREADS><<<grid, LN_THREADS, 0, rt.stream()>>>(xp, mp, vp, E, take_sqrt); break;
-    default: row_moments_kernel<float, 4, 4, 256><<<grid, 256, 0, rt.stream()>>>(xp, mp, vp, E, take_sqrt); break;
+    case 1: launch_pdl(row_moments_kernel<float, 4, 1, LN_THREADS>, dim3(grid), dim3(LN_THREADS), 0, rt.stream(), xp, mp, vp, E, take_sqrt); break;
+    case 2: launch_pdl(row_moments_kernel<float, 4, 2, LN_THREADS>, dim3(grid), dim3(LN_THREADS), 0, rt.stream(), xp, mp, vp, E, take_sqrt); break;
+    case 4: launch_pdl(row_moments_kernel<float, 4, 4, LN_THREADS>, dim3(grid), dim3(LN_THREADS), 0, rt.stream(), xp, mp, vp, E, take_sqrt); break;
+    default: launch_pdl(row_moments_kernel<float, 4, 4, 256>, dim3(grid), dim3(256), 0, rt.stream(), xp, mp, vp, E, take_sqrt); break;
     }
     rt.post_launch("row_moments_kernel");
     return true;
@@ -574,9 +577,18 @@ __device__ __forceinline__ void chan_merge(float &na, float &ma, float &sa, cons
 
 template <int VEC>
 __global__ void __cluster_dims__(1, CM_C, 1) __launch_bounds__(CM_WARPS * 32) col_moments_kernel(const ColMomentsArgs a) {
+    pdl_enter();
     __shared__ float w_mean[CM_WARPS][32 * VEC], w_m2[CM_WARPS][32 * VEC], w_n[CM_WARPS];
-    __shared__ float c_mean[32 * VEC], c_m2[32 * VEC], c_n;
+    __shared__ float in_mean[CM_C - 1][32 * VEC], in_m2[CM_C - 1][32 * VEC], in_n[CM_C - 1];  // cluster rank 0: the peers' folded triples
+    __shared__ uint64_t inbox_bar;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // rank 0 arms its inbox; the cluster barrier is only ARRIVED at here and waited for after the streaming loop (free by then): it
+    // orders the mbarrier init before the first remote store (the push fold of reduce_cols_kernel: one DSMEM hop, no cluster.sync)
+    if (tc::cluster_ctarank() == 0 && threadIdx.x == 0) {
+        tc::mbar_init(&inbox_bar, (uint32_t)(CM_C - 1) * 32 * VEC);
+        tc::fence_barrier_init();
+    }
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
     const int64_t o = blockIdx.z;
     const int64_t col0 = ((int64_t)blockIdx.x * 32 + lane) * VEC;
     const bool col_ok = col0 < a.inner;  // VEC > 1 only when inner % VEC == 0
@@ -587,28 +599,37 @@ __global__ void __cluster_dims__(1, CM_C, 1) __launch_bounds__(CM_WARPS * 32) co
     const int64_t r0 = (int64_t)blockIdx.y * CM_WARPS + warp, rstep = (int64_t)CM_C * CM_WARPS;
     if (col_ok) {
         int64_t r = r0;
-        // eight rows in flight per thread: the batch's own mean and centred second moment are formed from registers (two passes, all
-        // independent loads / adds), then folded into the running triple with one Chan update — no per-row dependency chain
-        constexpr int NB = 8;
-        for (; r + (NB - 1) * rstep < a.R; r += NB * rstep) {
-            float v[NB][VEC];
+        // Batches of four rows, double-buffered: the NEXT batch's loads are issued before the current batch's arithmetic, so a thread
+        // always has four to eight rows in flight (the first version loaded eight, waited, computed, and only then loaded again).
+        // A batch's own mean and centred second moment are formed from registers (all independent), then folded into the running
+        // triple with one Chan update — no per-row dependency chain, one reciprocal per batch.
+        constexpr int NB = 4;
+        float cur[NB][VEC], nxt[NB][VEC];
+        auto load_batch = [&](float (&v)[NB][VEC], int64_t rr) {
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
                 if (VEC == 4) {
-                    const float4 f = __ldcs(reinterpret_cast<const float4 *>(base + (r + b * rstep) * a.inner));
+                    const float4 f = __ldcs(reinterpret_cast<const float4 *>(base + (rr + b * rstep) * a.inner));
                     v[b][0] = f.x; v[b][VEC > 1 ? 1 : 0] = f.y; v[b][VEC > 2 ? 2 : 0] = f.z; v[b][VEC > 3 ? 3 : 0] = f.w;
                 } else {
-                    v[b][0] = __ldcs(base + (r + b * rstep) * a.inner);
+                    v[b][0] = __ldcs(base + (rr + b * rstep) * a.inner);
                 }
             }
+        };
+        bool have = r + (NB - 1) * rstep < a.R;
+        if (have) load_batch(cur, r);
+        while (have) {
+            const int64_t rn = r + NB * rstep;
+            const bool have_n = rn + (NB - 1) * rstep < a.R;
+            if (have_n) load_batch(nxt, rn);
             const float nn = n + (float)NB, f = (float)NB * __frcp_rn(nn);
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
-                const float bm = (((v[0][i] + v[1][i]) + (v[2][i] + v[3][i])) + ((v[4][i] + v[5][i]) + (v[6][i] + v[7][i]))) * (1.f / NB);
+                const float bm = ((cur[0][i] + cur[1][i]) + (cur[2][i] + cur[3][i])) * (1.f / NB);
                 float bs = 0.f;
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
-                    const float d = v[b][i] - bm;
+                    const float d = cur[b][i] - bm;
                     bs = fmaf(d, d, bs);
                 }
                 const float d = bm - mean[i];
@@ -616,6 +637,12 @@ __global__ void __cluster_dims__(1, CM_C, 1) __launch_bounds__(CM_WARPS * 32) co
                 m2[i] = m2[i] + bs + d * d * n * f;
             }
             n = nn;
+            r = rn;
+            have = have_n;
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) cur[b][i] = nxt[b][i];
         }
         for (; r < a.R; r += rstep) {
             float v0[VEC];
@@ -667,22 +694,23 @@ __global__ void __cluster_dims__(1, CM_C, 1) __launch_bounds__(CM_WARPS * 32) co
     if (tg == 0) {
 #pragma unroll
         for (int g = 1; g < NG; ++g) chan_merge(cn, cm, cs, w_n[g], w_mean[g][tc], w_m2[g][tc]);
-        c_mean[tc] = cm;
-        c_m2[tc] = cs;
-        if (tc == 0) c_n = cn;
     }
-    cg::cluster_group cluster = cg::this_cluster();
-    cluster.sync();
-    if (cluster.block_rank() == 0 && tg == 0) {
-        float pn[CM_C], pm[CM_C], ps[CM_C];  // every remote value is requested before the first merge
-#pragma unroll
-        for (unsigned rk = 1; rk < CM_C; ++rk) {
-            pn[rk] = *cluster.map_shared_rank(&c_n, rk);
-            pm[rk] = cluster.map_shared_rank(&c_mean[0], rk)[tc];
-            ps[rk] = cluster.map_shared_rank(&c_m2[0], rk)[tc];
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+    const uint32_t rank = tc::cluster_ctarank();
+    if (rank != 0) {  // push this CTA's triple into rank 0's inbox, arrive on its mbarrier (release), done
+        if (tg == 0) {
+            cg::cluster_group cluster = cg::this_cluster();
+            cluster.map_shared_rank(&in_mean[0][0], 0)[(rank - 1) * NCOL + tc] = cm;
+            cluster.map_shared_rank(&in_m2[0][0], 0)[(rank - 1) * NCOL + tc] = cs;
+            if (tc == 0) cluster.map_shared_rank(&in_n[0], 0)[rank - 1] = cn;
+            tc::mbar_arrive_cluster(tc::mapa_u32(&inbox_bar, 0));
         }
+        return;
+    }
+    if (tg == 0) {
+        tc::mbar_wait_cluster(&inbox_bar, 0);
 #pragma unroll
-        for (unsigned rk = 1; rk < CM_C; ++rk) chan_merge(cn, cm, cs, pn[rk], pm[rk], ps[rk]);
+        for (int rk = 0; rk < CM_C - 1; ++rk) chan_merge(cn, cm, cs, in_n[rk], in_mean[rk][tc], in_m2[rk][tc]);  // rank order
         const int64_t col = (int64_t)blockIdx.x * NCOL + tc;
         if (col < a.inner) {
             float second;
@@ -697,7 +725,6 @@ __global__ void __cluster_dims__(1, CM_C, 1) __launch_bounds__(CM_WARPS * 32) co
             a.out1[o * a.inner + col] = second;
         }
     }
-    cluster.sync();  // peers keep their shared memory alive until rank 0 has read it
 }
 
 bool launch_col_moments(const void *x, void *out0, void *out1, int dtype, int64_t outer, int64_t R, int64_t inner, int mode, bool take_sqrt,
@@ -714,8 +741,8 @@ bool launch_col_moments(const void *x, void *out0, void *out1, int dtype, int64_
     const int64_t strips = (inner + (vec4 ? 128 : 32) - 1) / (vec4 ? 128 : 32);
     KF_CHECK(strips < (int64_t)0x7FFFFFFF);
     const dim3 grid((unsigned)strips, CM_C, (unsigned)outer);
-    if (vec4) col_moments_kernel<4><<<grid, CM_WARPS * 32, 0, rt.stream()>>>(a);
-    else col_moments_kernel<1><<<grid, CM_WARPS * 32, 0, rt.stream()>>>(a);
+    if (vec4) launch_pdl(col_moments_kernel<4>, grid, dim3(CM_WARPS * 32), 0, rt.stream(), a);
+    else launch_pdl(col_moments_kernel<1>, grid, dim3(CM_WARPS * 32), 0, rt.stream(), a);
     rt.post_launch("col_moments_kernel");
     return true;
 }
@@ -752,7 +779,7 @@ static void ln_bwd_typed(const LnArgs &a, int ctas, bool write_dx) {
                 KF_CUDA(cudaFuncSetAttribute(layer_norm_bwd_ring_kernel<T, VEC, NVR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304)); \
                 attr_done = true;                                                                                               \
             }                                                                                                                   \
-            layer_norm_bwd_ring_kernel<T, VEC, NVR><<<ctas, 256, (size_t)(ring_stages * 2 * row_bytes), rt.stream()>>>(a, ring_stages); \
+            launch_pdl(layer_norm_bwd_ring_kernel<T, VEC, NVR>, dim3(ctas), dim3(256), (size_t)(ring_stages * 2 * row_bytes), rt.stream(), a, ring_stages); \
             break;                                                                                                              \
         }                                                                                                                       \
         if (write_dx && !two) {                                                                                                 \

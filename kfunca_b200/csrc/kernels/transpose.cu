@@ -11,6 +11,7 @@ constexpr int TT = 64;  // tile edge (elements)
 
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_tiled_kernel(const TransposePlan p, const int64_t tiles0, const int64_t tilesT) {
+    pdl_enter();
     __shared__ T tile[TT][TT + 1];
     int64_t bid = blockIdx.x;
     const int64_t t0 = bid % tiles0;
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(256) transpose_tiled_kernel(const TransposePla
 // out); the element transpose happens in shared memory.  Needs 16-byte aligned bases and vector-multiple strides.
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_vec_kernel(const TransposePlan p, const int64_t tiles0, const int64_t tilesT) {
+    pdl_enter();
     constexpr int VEC = 16 / sizeof(T);
     constexpr int PAD = sizeof(T) >= 4 ? 1 : 4 / sizeof(T);  // odd row pitch in 32-bit words
     constexpr int TPR = TT / VEC;                            // threads per tile row
@@ -119,19 +121,19 @@ void launch_transpose(const TransposePlan &p) {
     KF_CHECK(grid < (int64_t)0x7FFFFFFF, "transpose grid too large");
     if (transpose_vec_ok(p)) {
         switch (p.itemsize) {
-        case 1: transpose_vec_kernel<uint8_t><<<(unsigned)grid, 256, 0, rt.stream()>>>(p, tiles0, tilesT); break;
-        case 2: transpose_vec_kernel<uint16_t><<<(unsigned)grid, 256, 0, rt.stream()>>>(p, tiles0, tilesT); break;
-        case 4: transpose_vec_kernel<uint32_t><<<(unsigned)grid, 256, 0, rt.stream()>>>(p, tiles0, tilesT); break;
-        default: transpose_vec_kernel<uint64_t><<<(unsigned)grid, 256, 0, rt.stream()>>>(p, tiles0, tilesT); break;
+        case 1: launch_pdl(transpose_vec_kernel<uint8_t>, dim3((unsigned)grid), dim3(256), 0, rt.stream(), p, tiles0, tilesT); break;
+        case 2: launch_pdl(transpose_vec_kernel<uint16_t>, dim3((unsigned)grid), dim3(256), 0, rt.stream(), p, tiles0, tilesT); break;
+        case 4: launch_pdl(transpose_vec_kernel<uint32_t>, dim3((unsigned)grid), dim3(256), 0, rt.stream(), p, tiles0, tilesT); break;
+        default: launch_pdl(transpose_vec_kernel<uint64_t>, dim3((unsigned)grid), dim3(256), 0, rt.stream(), p, tiles0, tilesT); break;
         }
         rt.post_launch("transpose_vec_kernel");
         return;
     }
     switch (p.itemsize) {
-    case 1: transpose_tiled_kernel<uint8_t><<<(unsigned)grid, 256, 0, rt.stream()>>>(p, tiles0, tilesT); break;
-    case 2: transpose_tiled_kernel<uint16_t><<<(unsigned)grid, 256, 0, rt.stream()>>>(p, tiles0, tilesT); break;
-    case 4: transpose_tiled_kernel<uint32_t><<<(unsigned)grid, 256, 0, rt.stream()>>>(p, tiles0, tilesT); break;
-    default: transpose_tiled_kernel<uint64_t><<<(unsigned)grid, 256, 0, rt.stream()>>>(p, tiles0, tilesT); break;
+    case 1: launch_pdl(transpose_tiled_kernel<uint8_t>, dim3((unsigned)grid), dim3(256), 0, rt.stream(), p, tiles0, tilesT); break;
+    case 2: launch_pdl(transpose_tiled_kernel<uint16_t>, dim3((unsigned)grid), dim3(256), 0, rt.stream(), p, tiles0, tilesT); break;
+    case 4: launch_pdl(transpose_tiled_kernel<uint32_t>, dim3((unsigned)grid), dim3(256), 0, rt.stream(), p, tiles0, tilesT); break;
+    default: launch_pdl(transpose_tiled_kernel<uint64_t>, dim3((unsigned)grid), dim3(256), 0, rt.stream(), p, tiles0, tilesT); break;
     }
     rt.post_launch("transpose_tiled_kernel");
 }

@@ -585,8 +585,13 @@ def per_config(kf, Event, peaks, ref_cfg):
     cfgs[-1]["reference"] = {"note": "n/a (no backward in the reference)"}
     del q, kk, v, do, o, lse
     qf, kf32, vf = (rnd(10 + i, kf.float) for i in range(3))
-    ms_f32 = t(lambda i: kf.causal_attention(qf, kf32, vf), iters=2, warm=1)
-    tensor("c3_attention_fwd_fp32", ms_f32, fl, "attn_fwd_simt_kernel (fp32 FFMA parity path)")
+    ms_f32, ms_f32_min = t_calls(lambda i: kf.causal_attention(qf, kf32, vf))
+    os.environ["KF_ATTN_F32"] = "simt"
+    ms_f32_simt = t(lambda i: kf.causal_attention(qf, kf32, vf), iters=2, warm=1)
+    del os.environ["KF_ATTN_F32"]
+    tensor("c3_attention_fwd_fp32", ms_f32, fl, "split_planes_kernel x3 + attn_f32_tc_kernel<128> (tcgen05, fp32 via 3 bf16 planes, 6 products)",
+           {"ms_min": round(ms_f32_min, 4), "ours_simt_ms": round(ms_f32_simt, 3), "hardware_TFLOP/s_bf16": round(6 * fl / ms_f32 / 1e9, 1)})
+    cfgs[-1]["roofline"]["note"] = "frac = fp32 FLOP rate / bf16 dense peak; 6 bf16 MMAs per fp32 MMA on N = 64 score tiles: ~1/7 is the ceiling"
     cfgs[-1]["numpy"] = npb.get("c3_attention_fwd")
     del qf, kf32, vf
     # C5 block at one GPU (global batch 8 on this GPU); the N-GPU lines come from `--gpus N` (config.c5_block)

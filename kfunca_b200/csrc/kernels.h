@@ -123,6 +123,7 @@ struct AttnPlan {
 };
 void launch_attention_fwd(const AttnPlan &p);     // dispatcher: tcgen05 path for 16-bit D in {64,128}, else SIMT
 bool launch_attention_fwd_tc(const AttnPlan &p);  // false when the shape / dtype is not supported
+bool launch_attention_fwd_f32_tc(const AttnPlan &p);  // fp32 on tcgen05 (three bf16 planes per operand); false => FFMA kernel
 struct AttnBwdPlan {
     const void *q, *k, *v, *out, *dout;
     const void *lse;

@@ -131,6 +131,7 @@ static void attn_fwd_simt_typed(const AttnPlan &p) {
 
 void launch_attention_fwd(const AttnPlan &p) {
     if ((p.dtype == KF_HALF || p.dtype == KF_BFLOAT16) && launch_attention_fwd_tc(p)) return;
+    if (p.dtype == KF_FLOAT && launch_attention_fwd_f32_tc(p)) return;
     switch (p.dtype) {
     case KF_FLOAT: attn_fwd_simt_typed<float, float>(p); break;
     case KF_DOUBLE: attn_fwd_simt_typed<double, double>(p); break;

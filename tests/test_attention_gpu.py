@@ -45,6 +45,26 @@ def test_causal_attention_fp32_tight_and_fp64():
     np.testing.assert_allclose(out, O.causal_attention(q, k, v), rtol=1e-12, atol=1e-12)
 
 
+@pytest.mark.parametrize("shape,lo,hi,tol", [((1, 2, 256, 256, 128), -1, 1, 1e-5), ((1, 1, 200, 333, 128), -1, 1, 1e-5), ((2, 2, 640, 640, 64), -1, 1, 1e-5),
+                                             ((3, 5, 130, 130, 128), -1, 1, 1e-5), ((1, 3, 513, 257, 64), -1, 1, 1e-5), ((1, 2, 100, 700, 128), -1, 1, 1e-5),
+                                             ((1, 1, 2048, 2048, 128), 0, 1, 1e-5), ((2, 4, 32, 256, 128), -10, 10, 1e-3)])
+def test_causal_attention_fp32_tensor_core_path(shape, lo, hi, tol, monkeypatch):
+    """fp32 forward on tcgen05 (three bf16 planes per operand, attention_f32_tc.cu) against the float64 oracle at the fp32 band,
+    incl. an all-positive 2048-key case (every truncating addition of the tensor core has the same sign) and the reference's
+    U(-10, 10) inputs at its own tolerance; the FFMA kernel (KF_ATTN_F32=simt) must agree with it within the same band."""
+    q, k, v = qkv(*shape, lo=lo, hi=hi)
+    gq, gk, gv = g(q), g(k), g(v)
+    launches = kf.launch_count()
+    out, lse = kf.causal_attention_fwd(gq, gk, gv)
+    assert kf.launch_count() - launches == 4  # three plane splits + the tensor-core kernel: the path under test really ran
+    exact = O.causal_attention(q, k, v)
+    np.testing.assert_allclose(out.numpy(), exact, rtol=tol, atol=tol)
+    monkeypatch.setenv("KF_ATTN_F32", "simt")
+    out_s, lse_s = kf.causal_attention_fwd(gq, gk, gv)
+    np.testing.assert_allclose(out_s.numpy(), exact, rtol=tol, atol=tol)
+    np.testing.assert_allclose(lse.numpy(), lse_s.numpy(), rtol=1e-5, atol=1e-4 if hi > 1 else 1e-5)
+
+
 @pytest.mark.parametrize("name", ["attn_0", "attn_1", "attn_2"])
 def test_attention_against_reference_outputs(name):
     _, inp, _ = next((k, i, p) for n, k, i, p in cases() if n == name)

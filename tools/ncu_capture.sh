@@ -5,8 +5,8 @@ set -u
 tag=$1; shift
 fams=${@:-"ew reduce permute topk gemm attn"}
 mkdir -p gpurun_out
-declare -A KRE=( [ew]="ew_" [reduce]="reduce_" [permute]="transpose_" [topk]="topk_" [gemm]="gemm_tc2" [attn]="attn_fwd_tc" [attn_bwd]="attn_bwd" [gemm_f32]="gemm_f32x|split_f32" [norm]="moments|layer_norm" )
-declare -A CNT=( [ew]=2 [reduce]=5 [permute]=1 [topk]=2 [gemm]=1 [attn]=1 [attn_bwd]=3 [gemm_f32]=3 [norm]=4 )
+declare -A KRE=( [ew]="ew_" [reduce]="reduce_" [permute]="transpose_" [topk]="topk_" [gemm]="gemm_tc2" [attn]="attn_fwd_tc" [attn_bwd]="attn_bwd" [gemm_f32]="gemm_f32x|split_f32" [norm]="moments|layer_norm" [attn_f32]="attn_f32_tc|split_planes" [attn_pers]="attn_fwd_pers" )
+declare -A CNT=( [ew]=2 [reduce]=5 [permute]=1 [topk]=2 [gemm]=1 [attn]=1 [attn_bwd]=3 [gemm_f32]=3 [norm]=4 [attn_f32]=4 [attn_pers]=1 )
 for f in $fams; do
   out=gpurun_out/${tag}_${f}
   KF_PROF_REPS=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:${KRE[$f]} -c ${CNT[$f]} -f -o $out \

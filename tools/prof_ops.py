@@ -1,6 +1,6 @@
 """Profiling workload: one pass over each hot-path family at its BASELINE size (for `ncu`; never a bench number).
 
-  python tools/prof_ops.py [family ...]      families: ew reduce permute topk gemm gemm_f32 norm attn attn_bwd
+  python tools/prof_ops.py [family ...]      families: ew reduce permute topk gemm gemm_f32 norm attn attn_bwd attn_f32 attn_pers
 """
 import os
 import sys
@@ -81,5 +81,21 @@ if fams & {"attn", "attn_bwd"}:
         o, lse = kf.causal_attention_fwd(q, k, v)
         if "attn_bwd" in fams:
             kf.causal_attention_bwd(do, q, k, v, o, lse)
+if "attn_f32" in fams:  # C3 in fp32: three plane splits + the tcgen05 split-precision kernel
+    Bq, H, S, D = 8, 32, 4096, 128
+    q, k, v = (kf.empty([Bq, H, S, D], kf.float, 0) for _ in range(3))
+    for i, t in enumerate((q, k, v)):
+        t.random_uniform_(10 + i, -1.0, 1.0)
+    for _ in range(REPS):
+        kf.causal_attention_fwd(q, k, v)
+    del q, k, v
+if "attn_pers" in fams:  # the persistent forward kernel at the length it is the default for (S = 1024, same B H S as C3)
+    Bq, H, S, D = 32, 32, 1024, 128
+    q, k, v = (kf.empty([Bq, H, S, D], kf.bfloat16, 0) for _ in range(3))
+    for i, t in enumerate((q, k, v)):
+        t.random_uniform_(10 + i, -1.0, 1.0)
+    for _ in range(REPS):
+        kf.causal_attention_fwd(q, k, v)
+    del q, k, v
 kf.synchronize()
 print("prof_ops done")

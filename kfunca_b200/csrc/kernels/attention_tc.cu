@@ -730,6 +730,299 @@ __device__ __forceinline__ void attn_fwd_tc_body(const CUtensorMap &tmap_q, cons
 }
 
 // =====================================================================================================================
+// Forward with 64-KEY blocks and the next S issued BEFORE P V (KF_ATTN_FWD=k64).  In attn_fwd_tc_body P overwrites S in tensor
+// memory, so per tile  S(j) -> softmax(j) -> [P V(j), S(j+1)] -> softmax(j+1)  is one serial chain (2900 clk per 128 keys for the two
+// tiles against 2048 clk of tensor work).  With 64-key blocks tensor memory has room for S and P side by side —
+//   S0 | S1 (64 columns each) | P0 x2 | P1 x2 (32 columns each, double-buffered) | O0 | O1 = 512 columns —
+// so the issuer queues S_t(j+1) as soon as the softmax warps hold S_t(j) in registers (s_free) and P V_t(j) when P_t(j) is stored
+// (p_full): the tensor pipe always has the other tile's and the next block's work queued and never waits for a softmax, and a
+// softmax never waits for its own tile's P V.  Price: the score MMAs run at N = 64 (48 clk instead of 32 for half the columns: the
+// Q operand is re-read from shared memory for half as much math), 1280 clk of tensor work per 64 keys for the two tiles
+// (2560 per 128 keys).  P is double-buffered because P V_t(j - 1) may still be queued when softmax(j) stores; P V_t(j - 2) precedes
+// S_t(j) on the in-order pipe, so the buffer of block j - 2 is free once S_t(j) has been seen.  A rescale of O (row maximum grown
+// by more than 2^8) first waits for the tile's last P V (pv_done).
+template <int D, bool BF16, bool MASKED, int POLY>
+__device__ __forceinline__ void fwd_softmax_block64(const uint32_t s_addr, const uint32_t p_addr, const uint32_t o_addr, const float sc, const int lim,
+                                                    const bool first, float &m_ref, float &l_run, uint64_t *s_free, uint64_t *p_full,
+                                                    uint64_t *pv_done, const uint32_t pv_parity) {
+    uint32_t s[2][32];
+    tmem_ld32(s_addr, s[0]);
+    tmem_ld32(s_addr + 32, s[1]);
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(s_free);  // S is in registers: the issuer may queue the tile's next S
+    if (MASKED) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (c * 32 + i > lim) s[c][i] = 0xff800000u;  // -inf
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+            mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
+            mx1 = fmaxf(mx1, fmaxf(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])));
+            mx2 = fmaxf(mx2, fmaxf(__uint_as_float(s[c][i + 4]), __uint_as_float(s[c][i + 5])));
+            mx3 = fmaxf(mx3, fmaxf(__uint_as_float(s[c][i + 6]), __uint_as_float(s[c][i + 7])));
+        }
+    const float m_new = fmaxf(m_ref, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc);
+    const bool grow = first ? true : (m_new - m_ref > 8.f);  // lazy reference maximum, as in fwd_softmax_block
+    if (!first && __any_sync(0xffffffffu, grow)) {
+        mbar_wait(pv_done, pv_parity);  // the tile's previous P V may still be accumulating into O
+        tc_fence_after();
+        const float f = grow ? ((m_ref == -INFINITY) ? 0.f : ex2_approx(m_ref - m_new)) : 1.f;
+        l_run *= f;
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+            uint32_t orr[32];
+            tmem_ld32(o_addr + (uint32_t)(c * 32), orr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * f);
+            tmem_st32(o_addr + (uint32_t)(c * 32), orr);
+        }
+    }
+    if (grow) m_ref = m_new;
+    const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+    const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(-m_use, -m_use);
+    float2 rs2 = make_float2(0.f, 0.f), rs3 = make_float2(0.f, 0.f);
+    uint32_t pk[32];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            float2 x = __ffma2_rn(make_float2(__uint_as_float(s[h][i]), __uint_as_float(s[h][i + 1])), sc2, nm2);
+            if (((i >> 1) & 7) < POLY) {
+                x = ex2_poly2(x);
+            } else {
+                x.x = ex2_approx(x.x);
+                x.y = ex2_approx(x.y);
+            }
+            if (i & 2) rs3 = __fadd2_rn(rs3, x);
+            else rs2 = __fadd2_rn(rs2, x);
+            pk[h * 16 + (i >> 1)] = pack16t<BF16>(x);
+        }
+    tmem_st32(p_addr, pk);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(p_full);
+    l_run += (rs2.x + rs2.y) + (rs3.x + rs3.y);
+}
+
+template <int D, int POLY>
+__global__ void __launch_bounds__(FaCfg<1>::THREADS, 1)
+attn_fwd_k64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                    const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o, const AttnTcParams p) {
+    constexpr int ATOMS = D / 64;
+    constexpr int TILE_Q = 128 * D * 2, ATOM_Q = 128 * 128;  // a 128-row query tile / one of its 64-column atoms
+    constexpr int TILE_KV = 64 * D * 2, ATOM_KV = 64 * 128;  // a 64-row K or V tile
+    constexpr int BKV = 64, NS = 8;                           // ring: K_0, K_1, V_0, K_2, V_1, ... in consumption order
+    constexpr uint32_t TMEM_COLS = 512, P_COL = 128, O_COL = 256;
+    constexpr int W_MMA = 8, W_TMA = 9;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char *sQ = smem;
+    unsigned char *sKV = smem + 2 * TILE_Q;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sKV + NS * TILE_KV);
+    uint64_t *q_full = bars + 0;
+    uint64_t *kv_full = bars + 1, *kv_empty = bars + 1 + NS;
+    uint64_t *s_full = bars + 1 + 2 * NS;  // [2]
+    uint64_t *s_free = s_full + 2;         // [2]
+    uint64_t *p_full = s_free + 2;         // [2 tiles][2 P buffers]: a tile's softmax may store P(j + 1) before the issuer has looked at
+                                           // P(j) (it only needs S(j + 1), queued on s_free(j)); one barrier per buffer keeps a waiter
+                                           // at most one phase behind
+    uint64_t *pv_done = p_full + 4;        // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(pv_done + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int bh, pr;
+    fwd_decode_item(p, (int)blockIdx.x, bh, pr);
+    const int b_idx = bh / p.H, h_idx = bh % p.H;
+    const int q0 = pr * 2 * FA_BQ;
+    auto blocks_of = [&](int t) {
+        const int64_t q0t = (int64_t)q0 + t * FA_BQ;
+        const int64_t kv_end = min((int64_t)p.Skv, q0t + FA_BQ);
+        return q0t < p.Sq ? (int)((kv_end + BKV - 1) / BKV) : 0;
+    };
+    const int nblk0 = blocks_of(0), nblk1 = blocks_of(1);
+    const int nmax = max(nblk0, nblk1);
+
+    if (warp == W_TMA && lane == 0) {
+        prefetch_tmap(&tmap_q);
+        prefetch_tmap(&tmap_k);
+        prefetch_tmap(&tmap_v);
+        prefetch_tmap(&tmap_o);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&kv_empty[s], 1);
+        }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(&s_full[t], 1);
+            mbar_init(&s_free[t], 4);
+            mbar_init(&p_full[2 * t], 4);
+            mbar_init(&p_full[2 * t + 1], 4);
+            mbar_init(&pv_done[t], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == W_MMA) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= 8) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FaCfg<1>::REG_CTRL));
+      if (warp == W_TMA) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            const int ntile_q = nblk1 > 0 ? 2 : 1;
+            mbar_arrive_expect_tx(q_full, ntile_q * TILE_Q);
+            for (int t = 0; t < ntile_q; ++t)
+#pragma unroll
+                for (int a = 0; a < ATOMS; ++a) tma_load_4d(sQ + t * TILE_Q + a * ATOM_Q, &tmap_q, q_full, a * 64, q0 + t * FA_BQ, h_idx, b_idx);
+            int s = 0;
+            uint32_t ph = 0;
+            const int nloads = 2 * nmax;  // K_0, K_1, V_0, K_2, V_1, ..., K_{n-1}, V_{n-2}, V_{n-1}
+            for (int i = 0; i < nloads; ++i) {
+                const bool is_k = i == 0 || (i < nloads - 1 && (i & 1));
+                const int blk = i == 0 ? 0 : (is_k ? (i + 1) / 2 : (i == nloads - 1 ? nmax - 1 : i / 2 - 1));
+                const CUtensorMap *tm = is_k ? &tmap_k : &tmap_v;
+                mbar_wait(&kv_empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&kv_full[s], TILE_KV);
+#pragma unroll
+                for (int a = 0; a < ATOMS; ++a) tma_load_4d(sKV + s * TILE_KV + a * ATOM_KV, tm, &kv_full[s], a * 64, blk * BKV, h_idx, b_idx);
+                if (++s == NS) {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+        }
+        __syncwarp();
+      } else if (warp == W_MMA) {
+        // ===================================================== MMA issuer (converged warp, elected lane issues)
+        const bool leader = elect_one();
+        const int fmt = p.is_bf16 ? 1 : 0;
+        const uint32_t idesc_s = make_idesc_f16(fmt, 0, 0, FA_BQ, BKV);
+        const uint32_t idesc_pv = make_idesc_f16(fmt, 0, 1, FA_BQ, D);
+        const uint32_t q_addr = smem_u32(sQ), kv_addr = smem_u32(sKV);
+        auto issue_s = [&](int t, uint32_t k_addr) {
+#pragma unroll
+            for (int kk = 0; kk < D / 16; ++kk)
+                umma_f16_p(tmem_base + (uint32_t)(t * 64), make_sw128_desc(q_addr + t * TILE_Q + (uint32_t)((kk >> 2) * ATOM_Q + (kk & 3) * 32), 0, 1024),
+                           make_sw128_desc(k_addr + (uint32_t)((kk >> 2) * ATOM_KV + (kk & 3) * 32), 0, 1024), idesc_s, kk ? 1u : 0u, leader);
+        };
+        auto issue_pv = [&](int t, uint32_t v_addr, int j) {
+#pragma unroll
+            for (int kk = 0; kk < BKV / 16; ++kk)
+                umma_f16_ts_p(tmem_base + O_COL + (uint32_t)(t * D), tmem_base + P_COL + (uint32_t)(t * 64 + (j & 1) * 32 + kk * 8),
+                              make_sw128_desc(v_addr + kk * 2048, ATOM_KV, 1024), idesc_pv, (j > 0 || kk) ? 1u : 0u, leader);
+        };
+        int s = 0;
+        uint32_t ph = 0;
+        auto next_slot = [&]() {
+            mbar_wait(&kv_full[s], ph);
+            const int cur = s;
+            if (++s == NS) {
+                s = 0;
+                ph ^= 1;
+            }
+            return cur;
+        };
+        mbar_wait(q_full, 0);
+        {
+            const int sk = next_slot();  // K_0
+            tc_fence_after();
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+                if ((t ? nblk1 : nblk0) > 0) {
+                    issue_s(t, kv_addr + sk * TILE_KV);
+                    umma_commit_p(&s_full[t], leader);
+                }
+            umma_commit_p(&kv_empty[sk], leader);
+        }
+        for (int j = 0; j < nmax; ++j) {
+            if (j + 1 < nmax) {
+                const int sk = next_slot();  // K_{j+1}
+#pragma unroll
+                for (int t = 0; t < 2; ++t)
+                    if (j + 1 < (t ? nblk1 : nblk0)) {
+                        mbar_wait(&s_free[t], (uint32_t)(j & 1));  // S_t(j) is in the softmax warps' registers
+                        tc_fence_after();
+                        issue_s(t, kv_addr + sk * TILE_KV);
+                        umma_commit_p(&s_full[t], leader);
+                    }
+                umma_commit_p(&kv_empty[sk], leader);
+            }
+            const int sv = next_slot();  // V_j
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+                if (j < (t ? nblk1 : nblk0)) {
+                    mbar_wait(&p_full[2 * t + (j & 1)], (uint32_t)((j >> 1) & 1));
+                    tc_fence_after();
+                    issue_pv(t, kv_addr + sv * TILE_KV, j);
+                    umma_commit_p(&pv_done[t], leader);
+                }
+            umma_commit_p(&kv_empty[sv], leader);
+        }
+        __syncwarp();
+      }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FaCfg<1>::REG_SOFTMAX));
+        // ===================================================== softmax + epilogue: thread = one query row of tile t
+        const int t = warp >> 2, q = warp & 3;
+        const int n_t = t ? nblk1 : nblk0;
+        if (n_t > 0) {
+            const int r = q * 32 + lane;
+            const int64_t q0t = (int64_t)q0 + t * FA_BQ;
+            const int64_t m_row = q0t + r;
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+            const uint32_t s_addr = lane_addr + (uint32_t)(t * 64);
+            const uint32_t o_addr = lane_addr + O_COL + (uint32_t)(t * D);
+            const float sc = p.scale_log2;
+            float m_ref = -INFINITY, l_run = 0.f;
+            for (int j = 0; j < n_t; ++j) {
+                const int kv0 = j * BKV;
+                mbar_wait(&s_full[t], (uint32_t)(j & 1));
+                tc_fence_after();
+                const bool masked = (kv0 + BKV - 1 > q0t) || (kv0 + BKV > p.Skv);  // diagonal / ragged block (CTA-uniform per tile)
+                const int64_t lim64 = min(m_row, p.Skv - 1) - kv0;
+                const int lim = (int)max((int64_t)-1, min(lim64, (int64_t)63));
+                const uint32_t p_addr = lane_addr + P_COL + (uint32_t)(t * 64 + (j & 1) * 32);
+                const uint32_t pvp = (uint32_t)((j - 1) & 1);  // completion of the tile's previous P V (only looked at when j > 0)
+                if (p.is_bf16) {
+                    if (masked) fwd_softmax_block64<D, true, true, POLY>(s_addr, p_addr, o_addr, sc, lim, j == 0, m_ref, l_run, &s_free[t], &p_full[2 * t + (j & 1)], &pv_done[t], pvp);
+                    else fwd_softmax_block64<D, true, false, POLY>(s_addr, p_addr, o_addr, sc, lim, j == 0, m_ref, l_run, &s_free[t], &p_full[2 * t + (j & 1)], &pv_done[t], pvp);
+                } else {
+                    if (masked) fwd_softmax_block64<D, false, true, POLY>(s_addr, p_addr, o_addr, sc, lim, j == 0, m_ref, l_run, &s_free[t], &p_full[2 * t + (j & 1)], &pv_done[t], pvp);
+                    else fwd_softmax_block64<D, false, false, POLY>(s_addr, p_addr, o_addr, sc, lim, j == 0, m_ref, l_run, &s_free[t], &p_full[2 * t + (j & 1)], &pv_done[t], pvp);
+                }
+            }
+            // ---- epilogue: O / l -> 16-bit -> the tile's own (dead) Q buffer -> TMA store; row LSE
+            mbar_wait(&pv_done[t], (uint32_t)((n_t - 1) & 1));
+            tc_fence_after();
+            const float inv_l = 1.f / l_run;
+            const bool row_ok = m_row < p.Sq;
+            fwd_store_tile<D, ATOMS, false>(o_addr, inv_l, p.is_bf16, sQ + t * TILE_Q, &tmap_o, (int)q0t, h_idx, b_idx, r, 1 + t, nullptr);
+            if (row_ok && p.lse) p.lse[(int64_t)bh * p.Sq + m_row] = (m_ref + log2f(l_run)) * 0.6931471805599453f;
+            if (r == 0) tma_store_wait_all<0>();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == W_MMA) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// =====================================================================================================================
 // Forward, variant "P through shared memory" (KF_ATTN_FWD=ps): the next S of a tile no longer waits for the tile's P V.
 // In the kernel above P overwrites S in tensor memory, so the chain  S(j) -> softmax(j) -> [P V(j), S(j+1)] -> softmax(j+1)
 // is serial per tile: with two tiles ping-ponging, the tensor pipe has 2048 clk of work per KV block against a per-tile cycle of
@@ -1398,6 +1691,23 @@ static void launch_fwd_tc(const AttnPlan &a) {
         if (const char *e = std::getenv("KF_ATTN_HG")) hg = std::max(1, std::atoi(e));
         p.hg = (int)std::min<int64_t>(hg, a.BH);
     }
+    if constexpr (NH == 5) {  // 64-key blocks, next S issued before P V (attn_fwd_k64_kernel)
+        auto map64 = [&](const void *ptr, int64_t S, const AttnLayout &l) {
+            return make_tmap_4d_16bit(ptr, bf16, D, (uint64_t)S, (uint64_t)H, (uint64_t)B, (uint64_t)l.ss, (uint64_t)l.sh, (uint64_t)l.sb, 64, 64);
+        };
+        const CUtensorMap tk64 = map64(a.k, a.Skv, lk), tv64 = map64(a.v, a.Skv, lv);
+        constexpr int SMEM_K = 2 * 128 * D * 2 + 8 * 64 * D * 2 + 256 + 1024;
+        static bool attr_k = false;
+        if (!attr_k) {
+            KF_CUDA(cudaFuncSetAttribute(attn_fwd_k64_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_K));
+            attr_k = true;
+        }
+        const int64_t grid = a.BH * p.npairs;
+        KF_CHECK(grid < (int64_t)0x7FFFFFFF);
+        attn_fwd_k64_kernel<D, POLY><<<(unsigned)grid, FaCfg<1>::THREADS, SMEM_K, rt.stream()>>>(tq, tk64, tv64, to, p);
+        rt.post_launch("attn_fwd_k64_kernel");
+        return;
+    }
     if constexpr (NH == 4) {  // persistent kernel: one CTA per SM over the longest-first work list
         constexpr int SMEM_P = (2 + FA_NSTAGE) * 128 * D * 2 + 2 * 128 * 128 + 512 + 1024;  // tiles + epilogue staging + barriers, work queue + alignment slack
         static bool attr_p = false;
@@ -1503,10 +1813,12 @@ bool launch_attention_fwd_tc(const AttnPlan &a) {
     // pay for short items; for long ones the per-CTA kernel is as fast and simpler.
     const char *fwd_mode = std::getenv("KF_ATTN_FWD");
     const bool ps = fwd_mode && std::strcmp(fwd_mode, "ps") == 0;
+    const bool k64 = fwd_mode && std::strcmp(fwd_mode, "k64") == 0;
     const bool per_cta = fwd_mode ? std::strcmp(fwd_mode, "pers") != 0 : a.Skv > 2048;
 #define KF_FWD(DD, PP)                                                          \
     do {                                                                        \
         if (ps) launch_fwd_tc<DD, PP, 3>(a);                                    \
+        else if (k64) launch_fwd_tc<DD, PP, 5>(a);                              \
         else if (nh == 1 && !per_cta && !p_stale) launch_fwd_tc<DD, PP, 4>(a);  \
         else if (nh == 1) launch_fwd_tc<DD, PP, 1>(a);                          \
         else launch_fwd_tc<DD, PP, 2>(a);                                       \

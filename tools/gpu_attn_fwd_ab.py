@@ -33,7 +33,12 @@ for (b, h, sq, skv, d, cv) in [] if TRACE_ONLY else [(1, 2, 256, 256, 128, b16),
     o_p, l_p = run("pers", gq, gk, gv)
     o_c, l_c = run("cta", gq, gk, gv)
     same = np.array_equal(o_p, o_c) and np.array_equal(l_p, l_c)
-    msg = f"{b}x{h}x{sq}x{skv}x{d} {cv.__name__}: persistent == per-CTA bitwise: {same}"
+    o_k, l_k = run("k64", gq, gk, gv)
+    dk = float(np.abs(o_k - o_c).max())
+    dl = float(np.abs(l_k - l_c).max())
+    msg = f"{b}x{h}x{sq}x{skv}x{d} {cv.__name__}: persistent == per-CTA bitwise: {same}  k64 vs per-CTA max |d out| {dk:.3g} |d lse| {dl:.3g}"
+    if not (dk < 2e-2 and dl < 1e-3):
+        bad += 1
     if b * h * sq * skv <= 4 << 20:
         eo = O.causal_attention(q, k, v)
         err = np.abs(o_p - eo).max()
@@ -67,7 +72,7 @@ for S in () if TRACE_ONLY else (1024, 2048, 4096, 8192, 16384):
     fl = 4 * B * H * S * S * D / 2
     # the two kernels alternate call by call (the GPU is power-capped: clocks drift by 10 - 20 % over tens of milliseconds, so
     # back-to-back windows of one variant each are not comparable); per variant: minimum and median over the calls
-    times = {f"{m}:{hg}": [] for m in ("pers", "cta") for hg in ("1", "auto", "all")}  # heads per scheduling group (KF_ATTN_HG)
+    times = {f"{m}:{hg}": [] for m in ("pers", "cta", "k64") for hg in (("auto",) if "--hg" not in sys.argv else ("1", "auto", "all"))}  # heads per scheduling group (KF_ATTN_HG)
     evs = [Event() for _ in range(3)]
     for rep in range(16):
         for mode in times:

@@ -517,7 +517,7 @@ def per_config(kf, Event, peaks, ref_cfg):
     mem("c1_mean_dim0", lambda i: A[i].mean(0), nb + N * 4, "reduce_cols_kernel")
     mem("c1_mean_dim1", lambda i: A[i].mean(1), nb + N * 4, "reduce_rows_kernel")
     flat = [a_.view(-1) for a_ in A]
-    mem("c1_sum_all", lambda i: flat[i].sum(0), nb + 4, "reduce_rows_split_kernel")
+    mem("c1_sum_all", lambda i: flat[i].sum(0), nb + 4, "reduce_rows_kernel x2 (8192-element rows, then the 2048 row sums)")
     mem("c1_permute_contiguous", lambda i: A[i].permute(1, 0).contiguous(), 2 * nb, "transpose_vec_kernel")
     # statistics and fused norms over rows of 4096, fp32
     mem("f1_mean_var_dim1_fp32_4096", lambda i: A[i].mean_var(1, False), nb + 2 * N * 4, "row_moments_kernel")

@@ -767,6 +767,31 @@ static void reduce_typed(const ReducePlan &p) {
     int64_t factor_i = 1;
     if (p.is_mean && std::is_same<A, int64_t>::value) factor_i = (int64_t)p.factor;  // caller pre-computed the integer factor
     if (p.inner == 1) {
+        if constexpr (std::is_same<T, float>::value) {
+            // One long fp32 row (full-tensor sum / mean): two launches instead of one split kernel — rows of L elements through the
+            // plain row kernel (no cluster, no cross-CTA hand-shake: 0.91 of the HBM peak), then the R / L row sums (fp32, L2-resident)
+            // through the same code; with programmatic dependent launch the second launch overlaps the first one's drain.  Measured
+            // at 64 MiB: 12.9 us against 14.4 us for the split kernel with its last-CTA fold (KF_RED_TWOSTEP=0 keeps that one).
+            const char *off = std::getenv("KF_RED_TWOSTEP");
+            if (p.outer == 1 && p.R >= ((int64_t)1 << 22) && !(off && off[0] == '0')) {
+                int64_t L = 0;
+                for (int64_t cand : {8192, 4096, 2048, 1024})
+                    if (p.R % cand == 0 && p.R / cand >= 1024) {
+                        L = cand;
+                        break;
+                    }
+                if (L > 0) {
+                    const int64_t rows = p.R / L;
+                    Scratch partial((size_t)rows * sizeof(float));
+                    ReducePlan first = p, second = p;
+                    first.is_mean = 0;
+                    first.factor = 1.0;
+                    reduce_rows<float, float, float>(p.in, partial.p, rows, L, first, 1);
+                    reduce_rows<float, float, float>(partial.p, p.out, 1, rows, second, factor_i);  // applies the mean factor of the whole row
+                    return;
+                }
+            }
+        }
         reduce_rows<T, T, A>(p.in, p.out, p.outer, p.R, p, factor_i);
     } else {
         for (int64_t o0 = 0; o0 < p.outer; o0 += 65535) {

@@ -35,7 +35,6 @@ cases = [
     ("sum_dim1", lambda i: A[i].sum(1), nb + N * 4),
     ("mean_dim0", lambda i: A[i].mean(0), nb + N * 4),
     ("sum_all", lambda i: flat[i].sum(0), nb + 4),
-    ("sum_all_2step", lambda i: A[i].sum(1).view(-1).sum(0), nb + 4),
     ("permute", lambda i: A[i].permute(1, 0).contiguous(), 2 * nb),
     ("mean_var_dim1", lambda i: A[i].mean_var(1, False), nb + 2 * N * 4),
     ("norm_stat_dim0", lambda i: A[i].norm_stat(0), nb + 2 * N * 4),

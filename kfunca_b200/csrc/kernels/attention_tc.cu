@@ -615,7 +615,7 @@ __device__ __forceinline__ void attn_fwd_tc_body(const CUtensorMap &tmap_q, cons
                         mbar_wait(&p_full[2 * t], (uint32_t)((j - 1) & 1));
                         tc_fence_after();
                         issue_pv(t, kv_addr + sv * TILE_BYTES, j > 1, 0);
-                        umma_commit_p(&pv0_done[t], leader);
+                        if (p.stale) umma_commit_p(&pv0_done[t], leader);  // only the stale-reference softmax ever waits on it
                         mbar_wait(&p_full[2 * t + 1], (uint32_t)((j - 1) & 1));
                         tc_fence_after();
                         issue_pv(t, kv_addr + sv * TILE_BYTES, true, 1);

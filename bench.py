@@ -512,6 +512,12 @@ def per_config(kf, Event, peaks, ref_cfg):
     nb = N * N * 4
     mem("c1_add_fp32_4096", lambda i: A[i] + B[i], 3 * nb, "ew_pack_kernel")
     mem("c1_mul_fp32_4096", lambda i: A[i] * B[i], 3 * nb, "ew_pack_kernel")
+
+    def iadd(i):  # "also in-place a += b" (the values grow by b per call; fp32 stays finite over the 35 calls)
+        a_ = A[i]
+        a_ += B[i]
+
+    mem("c1_add_inplace_fp32_4096", iadd, 3 * nb, "ew_pack_kernel (output aliases the first input)")
     mem("c1_sum_dim0", lambda i: A[i].sum(0), nb + N * 4, "reduce_cols_kernel")
     mem("c1_sum_dim1", lambda i: A[i].sum(1), nb + N * 4, "reduce_rows_kernel")
     mem("c1_mean_dim0", lambda i: A[i].mean(0), nb + N * 4, "reduce_cols_kernel")

@@ -569,7 +569,7 @@ struct ColMomentsArgs {
 __device__ __forceinline__ void chan_merge(float &na, float &ma, float &sa, const float nb, const float mb, const float sb) {
     const float n = na + nb;
     if (nb == 0.f) return;
-    const float d = mb - ma, f = nb / n;
+    const float d = mb - ma, f = nb * __frcp_rn(n);  // counts are small integers: the product is within 1 ulp of nb / n, without the IEEE division sequence
     ma = fmaf(d, f, ma);
     sa = sa + sb + d * d * na * f;
     na = n;

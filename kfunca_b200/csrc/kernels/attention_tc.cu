@@ -134,22 +134,29 @@ __device__ __forceinline__ void fwd_softmax_block(const uint32_t s_addr, const u
     for (int c = 0; c < NC; ++c) tmem_ld32(s_addr + (uint32_t)(c * 32), s[c]);
     tmem_ld_wait();
     if (TR && tr) tr[0] = clock64();
+    // Diagonal / ragged blocks: 32-column chunks that are masked for EVERY row of this warp (warp q of the diagonal block keeps
+    // chunks 0 .. q only) take no mask, no maximum and no exponentials: their P is zero.  `nact` is warp-uniform.
+    const int nact = (MASKED && NH == 1) ? ((__reduce_max_sync(0xffffffffu, lim) + 32) >> 5) : NC;
     if (MASKED) {
 #pragma unroll
         for (int c = 0; c < NC; ++c)
+            if (c < nact) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (c * 32 + i > lim) s[c][i] = 0xff800000u;  // -inf
+                for (int i = 0; i < 32; ++i)
+                    if (c * 32 + i > lim) s[c][i] = 0xff800000u;  // -inf
+            }
     }
     float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
     for (int c = 0; c < NC; ++c)
+        if (c < nact) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-            mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
-            mx1 = fmaxf(mx1, fmaxf(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])));
-            mx2 = fmaxf(mx2, fmaxf(__uint_as_float(s[c][i + 4]), __uint_as_float(s[c][i + 5])));
-            mx3 = fmaxf(mx3, fmaxf(__uint_as_float(s[c][i + 6]), __uint_as_float(s[c][i + 7])));
+            for (int i = 0; i < 32; i += 8) {
+                mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
+                mx1 = fmaxf(mx1, fmaxf(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])));
+                mx2 = fmaxf(mx2, fmaxf(__uint_as_float(s[c][i + 4]), __uint_as_float(s[c][i + 5])));
+                mx3 = fmaxf(mx3, fmaxf(__uint_as_float(s[c][i + 6]), __uint_as_float(s[c][i + 7])));
+            }
         }
     float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
     if (NH == 2) {
@@ -182,20 +189,26 @@ __device__ __forceinline__ void fwd_softmax_block(const uint32_t s_addr, const u
     for (int c = 0; c < NC; c += 2) {
         uint32_t pk[32];
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < 2; ++h) {
+            if (c + h < nact) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-                float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c + h][i]), __uint_as_float(s[c + h][i + 1])), sc2, nm2);
-                if (((i >> 1) & 7) < POLY) {
-                    x = ex2_poly2(x);
-                } else {
-                    x.x = ex2_approx(x.x);
-                    x.y = ex2_approx(x.y);
+                for (int i = 0; i < 32; i += 2) {
+                    float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c + h][i]), __uint_as_float(s[c + h][i + 1])), sc2, nm2);
+                    if (((i >> 1) & 7) < POLY) {
+                        x = ex2_poly2(x);
+                    } else {
+                        x.x = ex2_approx(x.x);
+                        x.y = ex2_approx(x.y);
+                    }
+                    if (i & 2) rs3 = __fadd2_rn(rs3, x);  // two accumulators: half the dependent-add chain
+                    else rs2 = __fadd2_rn(rs2, x);
+                    pk[h * 16 + (i >> 1)] = pack16t<BF16>(x);
                 }
-                if (i & 2) rs3 = __fadd2_rn(rs3, x);  // two accumulators: half the dependent-add chain
-                else rs2 = __fadd2_rn(rs2, x);
-                pk[h * 16 + (i >> 1)] = pack16t<BF16>(x);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pk[h * 16 + i] = 0u;
             }
+        }
         if (TR && tr) tr[2 + c] = clock64() + (long long)(pk[31] == 0x12345u);
         tmem_st32(p_addr + (uint32_t)(c * 16), pk);
         // hand this 64-key half of P to the MMA warp right away: the first four k-steps of P V run under the second half's exps

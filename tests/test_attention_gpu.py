@@ -47,7 +47,8 @@ def test_causal_attention_fp32_tight_and_fp64():
 
 @pytest.mark.parametrize("shape,lo,hi,tol", [((1, 2, 256, 256, 128), -1, 1, 1e-5), ((1, 1, 200, 333, 128), -1, 1, 1e-5), ((2, 2, 640, 640, 64), -1, 1, 1e-5),
                                              ((3, 5, 130, 130, 128), -1, 1, 1e-5), ((1, 3, 513, 257, 64), -1, 1, 1e-5), ((1, 2, 100, 700, 128), -1, 1, 1e-5),
-                                             ((1, 1, 2048, 2048, 128), 0, 1, 1e-5), ((2, 4, 32, 256, 128), -10, 10, 1e-3)])
+                                             ((1, 1, 2048, 2048, 128), 0, 1, 1e-5), ((2, 4, 32, 256, 128), -10, 10, 1e-3),
+                                             ((1, 64, 1, 1024, 128), -1, 1, 1e-5), ((1, 2, 100, 5000, 64), -1, 1, 1e-5), ((1, 4, 129, 129, 128), -1, 1, 1e-5)])
 def test_causal_attention_fp32_tensor_core_path(shape, lo, hi, tol, monkeypatch):
     """fp32 forward on tcgen05 (three bf16 planes per operand, attention_f32_tc.cu) against the float64 oracle at the fp32 band,
     incl. an all-positive 2048-key case (every truncating addition of the tensor core has the same sign) and the reference's

@@ -12,7 +12,6 @@
 // The same role split as the forward: warp 9 = TMA producer, warp 8 = MMA issuer, warps 0-3 / 4-7 = element-wise math
 // of even / odd streamed tiles, so the tensor pipe works on one tile set while the other one is in its exp2 phase.
 // TMEM (512 columns): [set 0: T0 | T1] [set 1: T0 | T1] [ACC0 = dV] [ACC1 = dK or dQ].
-// delta = rowsum(dO o O) is formed by the MODE_DQ launch itself (it runs first; see the element-wise warps), not by a pre-pass.
 // Recomputing S and dP in both kernels costs 7 GEMMs instead of the fused scheme's 5, and buys bit-reproducible
 // gradients (no fp32 atomics on dQ) and two simple pipelines.
 #include <cmath>
@@ -31,9 +30,8 @@ enum { MODE_DKV = 0, MODE_DQ = 1 };
 
 struct AttnBwdTcParams {
     int64_t BH, Sq, Skv;
-    const float *lse;    // [BH, Sq] row log-sum-exp of the forward (natural log); used as lse * log2 e
-    float *delta;        // [BH, Sq] rowsum(dO o O): WRITTEN by the MODE_DQ launch (which runs first), read by MODE_DKV
-    const void *o, *dout;  // MODE_DQ: forward output and its gradient, dense [BH, Sq, D] (for delta)
+    const float *lse2;   // [BH, Sq] row log-sum-exp in the exp2 domain (lse * log2 e)
+    const float *delta;  // [BH, Sq] rowsum(dO o O)
     void *out0, *out1;   // MODE_DKV: dV, dK      MODE_DQ: unused, dQ
     float scale_log2;    // softmax scale * log2(e)
     float scale;         // softmax scale (applied to dK / dQ in the epilogue)
@@ -117,6 +115,28 @@ __device__ __forceinline__ void bwd_ew_tile(const uint32_t t_addr, const uint32_
     }
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// rowsum(dO o O) and the exp2-domain LSE.  16-byte loads: D/8 lanes per query row, 256/(D/8) rows per CTA (D = 64 / 128).
+template <typename T>
+__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const T *__restrict__ o, const T *__restrict__ dout, const float *__restrict__ lse,
+                                                            float *__restrict__ delta, float *__restrict__ lse2, const int64_t rows, const int D) {
+    const int lpr = D >> 3;  // lanes per row: 8 or 16
+    const int64_t row = (int64_t)blockIdx.x * (256 / lpr) + threadIdx.x / lpr;
+    const int sub = threadIdx.x % lpr;
+    float acc = 0.f;
+    if (row < rows) {
+        const uint4 vo = __ldg(reinterpret_cast<const uint4 *>(o + row * D) + sub);
+        const uint4 vd = __ldg(reinterpret_cast<const uint4 *>(dout + row * D) + sub);
+        const T *po = reinterpret_cast<const T *>(&vo), *pd = reinterpret_cast<const T *>(&vd);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc = fmaf(cvt_in<float>(po[i]), cvt_in<float>(pd[i]), acc);
+    }
+    for (int off = lpr >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (row < rows && sub == 0) {
+        delta[row] = acc;
+        lse2[row] = lse[row] * 1.4426950408889634f;
+    }
+}
 
 template <int D, int MODE>
 __global__ void __launch_bounds__(AB_THREADS, 1)
@@ -282,49 +302,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_con
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
         const uint32_t t_addr = lane_addr + (uint32_t)(set * 128);
         const float sc = p.scale_log2;
-        const float *lse = p.lse + (int64_t)bh * p.Sq;
-        float *delta = p.delta + (int64_t)bh * p.Sq;
+        const float *lse2 = p.lse2 + (int64_t)bh * p.Sq, *delta = p.delta + (int64_t)bh * p.Sq;
         float my_lse = 0.f, my_delta = 0.f;  // MODE_DQ: per-row scalars
-        if (MODE == MODE_DQ) {
-            // delta_i = rowsum(dO_i o O_i) of this CTA's 128 query rows, formed HERE (the separate pass over O and dO that used to
-            // precede both launches is gone: 0.55 GB and ~100 us at C3) while the first tiles are still on their way: D / 8 lanes
-            // per row read 16-byte pieces of O and dO (coalesced), shuffle-reduce, lane 0 of the group publishes the sum in
-            // shared memory (for both tile sets) and in global memory (for the MODE_DKV launch that follows).
-            constexpr int LPR = D / 8, RPW = 32 / LPR;  // lanes per row, rows per warp pass
-            const int sub = lane % LPR;
-            const uint16_t *po = reinterpret_cast<const uint16_t *>(p.o) + (int64_t)bh * p.Sq * D;
-            const uint16_t *pd = reinterpret_cast<const uint16_t *>(p.dout) + (int64_t)bh * p.Sq * D;
-            for (int rr = warp * RPW + lane / LPR; rr < 128; rr += 8 * RPW) {  // the eight element-wise warps share the 128 rows
-                const int64_t rg = (int64_t)x0_row + rr;
-                float acc = 0.f;
-                if (rg < p.Sq) {
-                    const uint4 vo = __ldg(reinterpret_cast<const uint4 *>(po + rg * D) + sub);
-                    const uint4 vd = __ldg(reinterpret_cast<const uint4 *>(pd + rg * D) + sub);
-                    const uint32_t wo[4] = {vo.x, vo.y, vo.z, vo.w}, wd[4] = {vd.x, vd.y, vd.z, vd.w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float2 fo, fd;
-                        if (p.is_bf16) {
-                            fo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&wo[i]));
-                            fd = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&wd[i]));
-                        } else {
-                            fo = __half22float2(*reinterpret_cast<const __half2 *>(&wo[i]));
-                            fd = __half22float2(*reinterpret_cast<const __half2 *>(&wd[i]));
-                        }
-                        acc = fmaf(fo.x, fd.x, acc);
-                        acc = fmaf(fo.y, fd.y, acc);
-                    }
-                }
-#pragma unroll
-                for (int off = LPR >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-                if (sub == 0) {
-                    svec[rr] = acc;
-                    if (rg < p.Sq) delta[rg] = acc;
-                }
-            }
-            named_bar_sync(3, 256);
-            my_delta = svec[r];
-            if (row_g < p.Sq) my_lse = lse[row_g] * 1.4426950408889634f;
+        if (MODE == MODE_DQ && row_g < p.Sq) {
+            my_lse = lse2[row_g];
+            my_delta = delta[row_g];
         }
         float *vec = svec + set * 256;  // [2 bufs][32 column pairs][-lse2 x2, -delta x2]
         const int tsel = threadIdx.x & 127;  // thread index inside the set
@@ -335,7 +317,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_con
             float v = 0.f;
             if (MODE == MODE_DKV && n < ntile) {
                 const int64_t qg = (int64_t)(t_lo + n) * 64 + (tsel & 63);
-                if (qg < p.Sq) v = tsel < 64 ? -lse[qg] * 1.4426950408889634f : -delta[qg];
+                if (qg < p.Sq) v = -(tsel < 64 ? lse2 : delta)[qg];
             }
             return v;
         };
@@ -423,7 +405,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_con
 }
 
 template <int D, int MODE>
-static void launch_bwd_mode(const AttnBwdPlan &a, float *delta) {
+static void launch_bwd_mode(const AttnBwdPlan &a, const float *lse2, const float *delta) {
     Runtime &rt = Runtime::get();
     const bool bf16 = a.dtype == KF_BFLOAT16;
     auto map = [&](const void *ptr, int64_t S, uint32_t rows) {
@@ -436,8 +418,7 @@ static void launch_bwd_mode(const AttnBwdPlan &a, float *delta) {
     const CUtensorMap y1 = MODE == MODE_DKV ? map(a.dout, a.Sq, 64) : map(a.v, a.Skv, 64);
     AttnBwdTcParams p{};
     p.BH = a.BH; p.Sq = a.Sq; p.Skv = a.Skv;
-    p.lse = reinterpret_cast<const float *>(a.lse); p.delta = delta;
-    p.o = a.out; p.dout = a.dout;
+    p.lse2 = lse2; p.delta = delta;
     p.out0 = a.dv;
     p.out1 = MODE == MODE_DKV ? a.dk : a.dq;
     const double scale = 1.0 / std::sqrt((double)D);
@@ -484,15 +465,23 @@ bool launch_attention_bwd_tc(const AttnBwdPlan &a) {
     if (!al(a.q) || !al(a.k) || !al(a.v) || !al(a.out) || !al(a.dout) || !al(a.dq) || !al(a.dk) || !al(a.dv)) return false;
     Runtime &rt = Runtime::get();
     const int64_t rows = a.BH * a.Sq;
-    // delta = rowsum(dO o O) is formed inside the dQ launch (one CTA per 128 query rows: exactly the rows it needs), which
-    // therefore runs FIRST; the dK / dV launch reads it.  No separate pass over O and dO.
-    Scratch delta((size_t)rows * 4);
+    Scratch delta((size_t)rows * 4), lse2((size_t)rows * 4);
+    const int64_t rows_per_cta = 256 / (a.D / 8);
+    KF_CHECK((rows + rows_per_cta - 1) / rows_per_cta < (int64_t)0x7FFFFFFF);
+    const unsigned pgrid = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
+    if (a.dtype == KF_BFLOAT16)
+        attn_bwd_prep_kernel<__nv_bfloat16><<<pgrid, 256, 0, rt.stream()>>>((const __nv_bfloat16 *)a.out, (const __nv_bfloat16 *)a.dout, (const float *)a.lse,
+                                                                            delta.as<float>(), lse2.as<float>(), rows, (int)a.D);
+    else
+        attn_bwd_prep_kernel<__half><<<pgrid, 256, 0, rt.stream()>>>((const __half *)a.out, (const __half *)a.dout, (const float *)a.lse, delta.as<float>(),
+                                                                     lse2.as<float>(), rows, (int)a.D);
+    rt.post_launch("attn_bwd_prep_kernel");
     if (a.D == 64) {
-        launch_bwd_mode<64, MODE_DQ>(a, delta.as<float>());
-        launch_bwd_mode<64, MODE_DKV>(a, delta.as<float>());
+        launch_bwd_mode<64, MODE_DKV>(a, lse2.as<float>(), delta.as<float>());
+        launch_bwd_mode<64, MODE_DQ>(a, lse2.as<float>(), delta.as<float>());
     } else {
-        launch_bwd_mode<128, MODE_DQ>(a, delta.as<float>());
-        launch_bwd_mode<128, MODE_DKV>(a, delta.as<float>());
+        launch_bwd_mode<128, MODE_DKV>(a, lse2.as<float>(), delta.as<float>());
+        launch_bwd_mode<128, MODE_DQ>(a, lse2.as<float>(), delta.as<float>());
     }
     return true;
 }

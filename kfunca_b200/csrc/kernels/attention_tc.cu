@@ -50,7 +50,7 @@ struct AttnTcParams {
     long long *trace;  // KF_ATTN_TRACE=1 (persistent kernel): clock64() stamps of CTA 0, [256 blocks][16] + [64 items][4] at 4096; else null
 };
 
-// Work item w -> (batch-head, query pair).  Heads are taken in groups of p.hg (a group's K and V fit in L2 together); inside a group
+// Work item w -> (batch-head, query pair).  Heads are taken in groups of p.hg (a group's K and V take ~ an eighth of the L2); inside a group
 // the items run length-major: every head's longest pair first, then the next length ... — longest-processing-time order for the
 // load balance, at most hg heads' K / V live at a time for the L2.  hg = BH: one global length-major list; hg = 1: head-major.
 __device__ __forceinline__ void fwd_decode_item(const AttnTcParams &p, const int w, int &bh, int &pr) {
@@ -1698,9 +1698,11 @@ static void launch_fwd_tc(const AttnPlan &a) {
         p.stale = (st && st[0] == '1') ? 1 : 0;
     }
     p.trace = nullptr;
-    {  // heads per scheduling group: as many as keep K + V of the group within ~half of the L2 (KF_ATTN_HG overrides, read per call)
+    {  // heads per scheduling group: K + V of a group ~ an eighth of the L2 (16 MB), the best of a sweep at S = 1024 / 4096 / 8192
+       // (tools/gpu_attn_hg_sweep.py: S = 4096 fastest call 1.058 ms head-major, 1.020 at 8 - 16 heads, 1.033 at 32, 1.174 for one
+       // global list; S = 8192 best at 4 heads, S = 1024 at >= 16).  KF_ATTN_HG overrides (read per call).
         const int64_t kv_bytes = 2 * a.Skv * D * 2;
-        int64_t hg = std::max<int64_t>(1, (int64_t)(rt.props().l2_bytes / 2) / std::max<int64_t>(1, kv_bytes));
+        int64_t hg = std::max<int64_t>(1, (int64_t)(rt.props().l2_bytes / 8) / std::max<int64_t>(1, kv_bytes));
         if (const char *e = std::getenv("KF_ATTN_HG")) hg = std::max(1, std::atoi(e));
         p.hg = (int)std::min<int64_t>(hg, a.BH);
     }

@@ -1702,7 +1702,10 @@ static void launch_fwd_tc(const AttnPlan &a) {
        // (tools/gpu_attn_hg_sweep.py: S = 4096 fastest call 1.058 ms head-major, 1.020 at 8 - 16 heads, 1.033 at 32, 1.174 for one
        // global list; S = 8192 best at 4 heads, S = 1024 at >= 16).  KF_ATTN_HG overrides (read per call).
         const int64_t kv_bytes = 2 * a.Skv * D * 2;
-        int64_t hg = std::max<int64_t>(1, (int64_t)(rt.props().l2_bytes / 8) / std::max<int64_t>(1, kv_bytes));
+        // the persistent kernel (short sequences: everything fits the L2 anyway) prefers the longer longest-first runs of big groups:
+        // S = 1024, 126 heads per group 0.388 ms, 31 heads 0.432 ms (gpurun_out/r6c, r21)
+        const int64_t budget = (int64_t)rt.props().l2_bytes / (NH == 4 ? 2 : 8);
+        int64_t hg = std::max<int64_t>(1, budget / std::max<int64_t>(1, kv_bytes));
         if (const char *e = std::getenv("KF_ATTN_HG")) hg = std::max(1, std::atoi(e));
         p.hg = (int)std::min<int64_t>(hg, a.BH);
     }

@@ -194,6 +194,11 @@ int kf_rms_norm(kf_tensor_t x, kf_tensor_t gain, double eps, kf_tensor_t *out);
 /* ---- fused linear ops (ref: README.md:32 `qkv_linear`, src/core/gemm_ops.cpp:6-16) ---------------------- */
 /* out = alpha * a[...,K] @ b[K,N] + residual[...,N]: the residual add runs in the GEMM epilogue; bit-identical to kf_gemm + kf_binary(ADD) */
 int kf_gemm_residual(kf_tensor_t a, kf_tensor_t b, kf_tensor_t residual, float alpha, kf_tensor_t *out);
+/* out[..., N] = x[..., K] @ w[K, N] + bias[N] (bias may be NULL): the projection the reference's README lists as its next operator
+ * (ref: README.md:32 `qkv_linear`; it would sit on gpu::gemm, src/core/gemm_ops.cpp:6-16).  The bias row is added in the GEMM epilogue;
+ * bit-identical to kf_gemm followed by a broadcast kf_binary(ADD); differentiable in x, w and bias.  Feed the result to
+ * kf_qkv_attention to run attention on the packed projection in place. */
+int kf_qkv_linear(kf_tensor_t x, kf_tensor_t w, kf_tensor_t bias, kf_tensor_t *out);
 /* out = (a @ b1) * (a @ b3), the bilinear GLU, as ONE dual-B tcgen05 kernel (fp16 / bf16; other dtypes and small shapes are composed) */
 int kf_gemm_glu(kf_tensor_t a, kf_tensor_t b1, kf_tensor_t b3, kf_tensor_t *out);
 

@@ -59,7 +59,7 @@ class Block:
         B, S, E = x.sizes()
         H, D = self.H, self.D
         xn = self.norm(x, p["g1"])
-        qkv = kf.gemm(xn, p["wqkv"], 1.0, 0.0)
+        qkv = kf.qkv_linear(xn, p["wqkv"], None) if self.fused else kf.gemm(xn, p["wqkv"], 1.0, 0.0)  # README.md:32 (no bias in this block)
         if self.fused and hasattr(kf, "qkv_attention"):
             o = kf.qkv_attention(qkv, H)  # [B, S, 3E] -> [B, S, E]
         else:

@@ -602,6 +602,11 @@ int kf_gemm_residual(kf_tensor_t a, kf_tensor_t b, kf_tensor_t residual, float a
     *out = wrap(ops::gemm_residual(T(a), T(b), T(residual), alpha));
     KF_API_END
 }
+int kf_qkv_linear(kf_tensor_t x, kf_tensor_t w, kf_tensor_t bias, kf_tensor_t *out) {
+    KF_API_BEGIN
+    *out = wrap(ops::qkv_linear(T(x), T(w), bias ? T(bias) : Tensor()));
+    KF_API_END
+}
 int kf_gemm_glu(kf_tensor_t a, kf_tensor_t b1, kf_tensor_t b3, kf_tensor_t *out) {
     KF_API_BEGIN
     *out = wrap(ops::gemm_glu(T(a), T(b1), T(b3)));

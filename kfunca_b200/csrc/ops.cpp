@@ -766,7 +766,7 @@ struct MatmulGrad : GradFunction {
 
 static thread_local int64_t g_route_M = 0;  // set by gemm_host around its slab products (GemmPlan::route_M)
 static Tensor matmul_nograd(const Tensor &a, bool ta, const Tensor &b, bool tb, float alpha, float beta, Tensor *out_opt,
-                            const Tensor *residual = nullptr) {
+                            const Tensor *residual = nullptr, bool residual_is_row = false) {
     require_device(a, "matmul");
     require_device(b, "matmul");
     KF_CHECK(a.dtype() == b.dtype(), "matmul: dtype mismatch");
@@ -817,11 +817,12 @@ static Tensor matmul_nograd(const Tensor &a, bool ta, const Tensor &b, bool tb, 
     p.beta = beta;
     Tensor rh;
     if (residual) {
-        KF_CHECK(residual->dtype() == a.dtype() && residual->numel() == out.numel(), "gemm_residual: residual must match the output");
+        KF_CHECK(residual->dtype() == a.dtype() && residual->numel() == (residual_is_row ? p.N : out.numel()),
+                 "gemm_residual: residual must match the output (or one row of it)");
         rh = residual->is_contiguous() ? *residual : clone(residual->detach());
         p.residual = rh.data();
-        p.ldr = p.N;
-        p.sr = p.M * p.N;
+        p.ldr = residual_is_row ? 0 : p.N;  // a bias row: every output row adds the same N values (row and batch strides 0)
+        p.sr = residual_is_row ? 0 : p.M * p.N;
     }
     if (out.numel() > 0) launch_gemm(p);
     return out;
@@ -900,6 +901,45 @@ Tensor gemm_residual(const Tensor &a, const Tensor &b, const Tensor &residual, f
         fn->alpha = alpha;
         fn->b_shared = a.dim() > 2;
         attach(out, fn, {a, b, residual});
+    }
+    return out;
+}
+
+struct LinearBiasGrad : MatmulGrad {  // inputs: x, w, bias
+    std::vector<int64_t> bias_shape;
+    const char *name() const override { return "LinearBiasGrad"; }
+    std::vector<Tensor> backward(const Tensor &g) override {
+        std::vector<Tensor> r = MatmulGrad::backward(g);
+        Tensor db;
+        if (inputs[2].requires_grad()) {
+            Tensor g2 = g.contiguous().view({-1, g.size(-1)});
+            db = sum(g2, 0).view(bias_shape);  // column sums over every row of every batch entry (fp32 accumulation)
+        }
+        r.push_back(db);
+        return r;
+    }
+};
+
+// y[..., N] = x[..., K] @ w[K, N] (+ bias[N]): the projection the reference's README names as its next op (README.md:32 `qkv_linear`,
+// on top of gpu::gemm, src/core/gemm_ops.cpp:6-16).  The bias row is added in the GEMM epilogue (residual pointer with row stride
+// 0): bit-identical to gemm followed by a broadcast add.  `bias` may be undefined (plain projection).
+Tensor qkv_linear(const Tensor &x, const Tensor &w, const Tensor &bias) {
+    if (!bias.defined()) return matmul(x, false, w, false, 1.f);
+    KF_CHECK(x.is_contiguous() && w.is_contiguous(), "qkv_linear: operands must be contiguous");
+    KF_CHECK(w.dim() == 2 && x.dim() >= 2 && w.size(0) == x.size(-1), "qkv_linear: w must be [K, N]");
+    KF_CHECK(x.dtype() == w.dtype() && x.dtype() == bias.dtype(), "qkv_linear: dtype mismatch");
+    KF_CHECK(bias.numel() == w.size(1), "qkv_linear: bias must have N = ", w.size(1), " elements");
+    Tensor out = matmul_nograd(x, false, w, false, 1.f, 0.f, nullptr, &bias, true);
+    if (any_requires_grad({&x, &w, &bias})) {
+        auto *fn = new LinearBiasGrad();
+        fn->a = x.detach();
+        fn->b = w.detach();
+        fn->ta = false;
+        fn->tb = false;
+        fn->alpha = 1.f;
+        fn->b_shared = x.dim() > 2;
+        fn->bias_shape = bias.sizes();
+        attach(out, fn, {x, w, bias});
     }
     return out;
 }

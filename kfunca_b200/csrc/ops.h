@@ -67,6 +67,7 @@ void gemm_out(Tensor &out, const Tensor &a, const Tensor &b, float alpha, float 
 Tensor matmul(const Tensor &a, bool trans_a, const Tensor &b, bool trans_b, float alpha);
 // fused epilogues: alpha * a @ b + residual, and the GLU product gemm(a, b1) * gemm(a, b3); bit-identical to the composed forms
 Tensor gemm_residual(const Tensor &a, const Tensor &b, const Tensor &residual, float alpha);
+Tensor qkv_linear(const Tensor &x, const Tensor &w, const Tensor &bias);  // bias may be undefined
 Tensor gemm_glu(const Tensor &a, const Tensor &b1, const Tensor &b3);
 // operands and result in (pinned) host memory; uploads, slab products and downloads overlap on three streams
 void gemm_host(const void *a_host, const void *b_host, void *c_host, int64_t M, int64_t N, int64_t K, DType dtype, float alpha,

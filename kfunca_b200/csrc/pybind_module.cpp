@@ -339,6 +339,11 @@ PYBIND11_MODULE(_kfunca, m) {
         ck(kf_gemm_residual(a.get(), b.get(), r.get(), alpha, &h));
         return PyTensor(h);
     });
+    m.def("qkv_linear", [](const PyTensor &x, const PyTensor &w, py::object bias) {  // bias: tensor or None
+        kf_tensor_t h;
+        ck(kf_qkv_linear(x.get(), w.get(), bias.is_none() ? nullptr : bias.cast<const PyTensor &>().get(), &h));
+        return PyTensor(h);
+    }, py::arg("x"), py::arg("w"), py::arg("bias") = py::none());
     m.def("gemm_glu", [](const PyTensor &a, const PyTensor &b1, const PyTensor &b3) {
         kf_tensor_t h;
         ck(kf_gemm_glu(a.get(), b1.get(), b3.get(), &h));

@@ -107,6 +107,45 @@ def test_gemm_residual_is_bit_identical_to_gemm_then_add(dt, shape):
     assert np.array_equal(fused.numpy().view(np.uint8), composed.numpy().view(np.uint8))
 
 
+@pytest.mark.parametrize("dt", ["bfloat16", "half", "float", "double"])
+@pytest.mark.parametrize("shape", [(512, 256, 384), (130, 264, 1032), (2, 300, 128, 768), (3, 7, 16, 24)])
+def test_qkv_linear_bias_in_the_epilogue(dt, shape):
+    """qkv_linear(x, w, bias) (ref: README.md:32, the reference's next planned operator): the bias row added in the GEMM epilogue is
+    bit-identical to gemm followed by a broadcast add, matches the float64 oracle, and without a bias it IS gemm."""
+    *lead, k, n = shape
+    kdt = getattr(kf, dt)
+    x = g(RNG.uniform(-1, 1, (*lead, k)).astype(np.float32)).to(kdt)
+    w = g(RNG.uniform(-1, 1, (k, n)).astype(np.float32)).to(kdt)
+    brow = RNG.uniform(-1, 1, (n,)).astype(np.float32)
+    bias = g(brow).to(kdt)
+    fused = kf.qkv_linear(x, w, bias)
+    plain = kf.gemm(x, w, 1.0, 0.0)
+    composed = plain + bias.view(*([1] * len(lead)), n)
+    assert fused.sizes() == [*lead, n]
+    assert np.array_equal(fused.numpy().view(np.uint8), composed.numpy().view(np.uint8))
+    assert np.array_equal(kf.qkv_linear(x, w, None).numpy().view(np.uint8), plain.numpy().view(np.uint8))
+    xs, ws, bs = (t.double().numpy() if dt == "double" else t.float().numpy().astype(np.float64) for t in (x, w, bias))
+    exact = xs @ ws + bs
+    tol = {"bfloat16": 2e-2, "half": 2e-2, "float": 1e-5, "double": 1e-12}[dt]
+    mass = np.abs(xs) @ np.abs(ws) + np.abs(bs)
+    got = fused.double().numpy() if dt == "double" else fused.float().numpy().astype(np.float64)
+    assert np.all(np.abs(got - exact) <= tol * mass + (2e-2 * np.abs(exact) if tol > 1e-3 else 0))
+
+
+def test_qkv_linear_gradients():
+    m, k, n = 3 * 128, 256, 384
+    mk = lambda shape: g(RNG.uniform(-1, 1, shape).astype(np.float32))
+    x, w, b, go = mk((2, m // 2, k)), mk((k, n)), mk((n,)), mk((2, m // 2, n))
+    for t in (x, w, b):
+        t.set_requires_grad(True)
+    kf.qkv_linear(x, w, b).backward(go)
+    xn, wn, gn = x.numpy().reshape(m, k).astype(np.float64), w.numpy().astype(np.float64), go.numpy().reshape(m, n).astype(np.float64)
+    np.testing.assert_allclose(x.grad().numpy().reshape(m, k), gn @ wn.T, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(w.grad().numpy(), xn.T @ gn, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(b.grad().numpy().reshape(n), gn.sum(0), rtol=1e-4, atol=1e-4)
+    assert b.grad().sizes() == [n]
+
+
 @pytest.mark.parametrize("dt", ["bfloat16", "half"])
 @pytest.mark.parametrize("shape", [(512, 256, 384), (300, 264, 1032), (2, 300, 128, 256), (64, 64, 64)])
 def test_gemm_glu_is_bit_identical_to_two_gemms_and_a_multiply(dt, shape):

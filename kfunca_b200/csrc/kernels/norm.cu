@@ -556,7 +556,7 @@ bool launch_row_moments(const void *x, void *mean, void *var, int dtype, int64_t
 // row shared by its VEC columns), the 8 warps merge through shared memory (Chan's pairwise update, fixed order), the CTAs merge
 // through distributed shared memory in rank order: deterministic, no atomics, no staging buffer, no semaphore (the reference's
 // un-zeroed semaphore block, SURVEY F10, has no counterpart).
-constexpr int CM_C = 8, CM_WARPS = 16;  // 16 warps: half as many rows per thread, twice the loads in flight per SM (ncu: 22 % occupancy at 8)
+constexpr int CM_C = 8;
 
 struct ColMomentsArgs {
     const float *x;
@@ -575,28 +575,34 @@ __device__ __forceinline__ void chan_merge(float &na, float &ma, float &sa, cons
     na = n;
 }
 
-template <int VEC>
-__global__ void __cluster_dims__(1, CM_C, 1) __launch_bounds__(CM_WARPS * 32) col_moments_kernel(const ColMomentsArgs a) {
+// LPR lanes run along the contiguous dim (a warp covers 32 / LPR rows per load), WARPS warps per CTA; WARPS * 32 / LPR = 16 row
+// slots per CTA in every geometry.  <4, 16, 8>: 64-column strips, 256 threads, twice as many (narrower) CTAs — the geometry of
+// reduce_cols_kernel; <4, 32, 16> / <1, 32, 16>: 128- / 32-column strips, 512 threads.
+template <int VEC, int LPR, int WARPS>
+__global__ void __cluster_dims__(1, CM_C, 1) __launch_bounds__(WARPS * 32) col_moments_kernel(const ColMomentsArgs a) {
     pdl_enter();
-    __shared__ float w_mean[CM_WARPS][32 * VEC], w_m2[CM_WARPS][32 * VEC], w_n[CM_WARPS];
-    __shared__ float in_mean[CM_C - 1][32 * VEC], in_m2[CM_C - 1][32 * VEC], in_n[CM_C - 1];  // cluster rank 0: the peers' folded triples
+    constexpr int RPW = 32 / LPR, SLOTS = WARPS * RPW, NCOL = LPR * VEC;
+    static_assert(SLOTS == 16, "the two-level fold below merges 4 x 4 row slots");
+    __shared__ float w_mean[SLOTS][NCOL], w_m2[SLOTS][NCOL], w_n[SLOTS];
+    __shared__ float in_mean[CM_C - 1][NCOL], in_m2[CM_C - 1][NCOL], in_n[CM_C - 1];  // cluster rank 0: the peers' folded triples
     __shared__ uint64_t inbox_bar;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // rank 0 arms its inbox; the cluster barrier is only ARRIVED at here and waited for after the streaming loop (free by then): it
     // orders the mbarrier init before the first remote store (the push fold of reduce_cols_kernel: one DSMEM hop, no cluster.sync)
     if (tc::cluster_ctarank() == 0 && threadIdx.x == 0) {
-        tc::mbar_init(&inbox_bar, (uint32_t)(CM_C - 1) * 32 * VEC);
+        tc::mbar_init(&inbox_bar, (uint32_t)(CM_C - 1) * NCOL);
         tc::fence_barrier_init();
     }
     asm volatile("barrier.cluster.arrive.release;" ::: "memory");
     const int64_t o = blockIdx.z;
-    const int64_t col0 = ((int64_t)blockIdx.x * 32 + lane) * VEC;
+    const int cl = lane % LPR, slot = warp * RPW + lane / LPR;
+    const int64_t col0 = ((int64_t)blockIdx.x * LPR + cl) * VEC;
     const bool col_ok = col0 < a.inner;  // VEC > 1 only when inner % VEC == 0
     const float *__restrict__ base = a.x + o * a.R * a.inner + col0;
     float n = 0.f, mean[VEC], m2[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) mean[i] = m2[i] = 0.f;
-    const int64_t r0 = (int64_t)blockIdx.y * CM_WARPS + warp, rstep = (int64_t)CM_C * CM_WARPS;
+    const int64_t r0 = (int64_t)blockIdx.y * SLOTS + slot, rstep = (int64_t)CM_C * SLOTS;
     if (col_ok) {
         int64_t r = r0;
         // Batches of four rows, double-buffered: the NEXT batch's loads are issued before the current batch's arithmetic, so a thread
@@ -664,17 +670,17 @@ __global__ void __cluster_dims__(1, CM_C, 1) __launch_bounds__(CM_WARPS * 32) co
     }
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-        w_mean[warp][lane * VEC + i] = mean[i];
-        w_m2[warp][lane * VEC + i] = m2[i];
+        w_mean[slot][cl * VEC + i] = mean[i];
+        w_m2[slot][cl * VEC + i] = m2[i];
     }
-    // the row count of a warp does not depend on the column: lanes without a valid column report the count too (uniform merge)
-    if (lane == 0) w_n[warp] = r0 < a.R ? (float)((a.R - r0 + rstep - 1) / rstep) : 0.f;
+    // the row count of a slot does not depend on the column: lanes without a valid column report the count too (uniform merge)
+    if (cl == 0) w_n[slot] = r0 < a.R ? (float)((a.R - r0 + rstep - 1) / rstep) : 0.f;
     __syncthreads();
     // Fold in two levels, ONE COLUMN PER THREAD (the first version let warp 0 walk all 15 other warps for its VEC columns per lane:
     // 60 dependent Chan updates, each with a division — 3.7 us of an 18 us kernel).  Level 1: thread (g, c) merges warps 4g .. 4g + 3
-    // of column c (g = 0 .. CM_WARPS / 4 - 1); level 2: threads of group 0 merge the group results.  Fixed order: deterministic.
-    constexpr int NCOL = 32 * VEC, NG = CM_WARPS / 4;
-    static_assert(NCOL * NG <= CM_WARPS * 32, "one (group, column) per thread");
+    // of column c (g = 0 .. 3: row slots 4g .. 4g + 3); level 2: threads of group 0 merge the group results.  Fixed order: deterministic.
+    constexpr int NG = 4;
+    static_assert(NCOL * NG <= WARPS * 32, "one (group, column) per thread");
     const int tc = threadIdx.x % NCOL, tg = threadIdx.x / NCOL;
     float cn = 0.f, cm = 0.f, cs = 0.f;
     if (tg < NG) {
@@ -738,11 +744,17 @@ bool launch_col_moments(const void *x, void *out0, void *out1, int dtype, int64_
     a.outer = outer; a.R = R; a.inner = inner;
     a.eps = (float)eps; a.mode = mode; a.take_sqrt = take_sqrt ? 1 : 0;
     const bool vec4 = inner % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0;
-    const int64_t strips = (inner + (vec4 ? 128 : 32) - 1) / (vec4 ? 128 : 32);
+    // KF_CM_GEOM=narrow: 64-column strips, 256 threads, twice the CTAs (the geometry of reduce_cols_kernel).  Measured at 4096 x 4096:
+    // 19.7 us against 15.4 us for the default 128-column strips with 512 threads, so it stays an A/B switch.
+    const char *geom = std::getenv("KF_CM_GEOM");
+    const bool narrow = vec4 && geom && std::strcmp(geom, "narrow") == 0;
+    const int64_t width = vec4 ? (narrow ? 64 : 128) : 32;
+    const int64_t strips = (inner + width - 1) / width;
     KF_CHECK(strips < (int64_t)0x7FFFFFFF);
     const dim3 grid((unsigned)strips, CM_C, (unsigned)outer);
-    if (vec4) launch_pdl(col_moments_kernel<4>, grid, dim3(CM_WARPS * 32), 0, rt.stream(), a);
-    else launch_pdl(col_moments_kernel<1>, grid, dim3(CM_WARPS * 32), 0, rt.stream(), a);
+    if (narrow) launch_pdl(col_moments_kernel<4, 16, 8>, grid, dim3(256), 0, rt.stream(), a);
+    else if (vec4) launch_pdl(col_moments_kernel<4, 32, 16>, grid, dim3(512), 0, rt.stream(), a);
+    else launch_pdl(col_moments_kernel<1, 32, 16>, grid, dim3(512), 0, rt.stream(), a);
     rt.post_launch("col_moments_kernel");
     return true;
 }
